@@ -1,0 +1,110 @@
+/* libntt256 -- B200-native (sm_100a) forward/inverse NTT over 256-bit prime fields.
+ *
+ * Drop-in boundary for the 256-bit NTT path of tie-pilot-qxw/NTT.  The reference has no
+ * library API: its boundary is the C++ host drivers called from main(),
+ *
+ *   template<uint tpi,uint bits> void NTT_GZKP(cgbn_mem_t<bits> data[], uint len, uint2 reverse[],
+ *       uint reverse_len, cgbn_mem_t<bits> prime, cgbn_mem_t<bits> omega, uint B, uint G)
+ *                                                     (/root/reference/src/big-num.cu:260-353)
+ *   template<uint tpi,uint bits> void NTT_GPU_Naive(...)              (big-num.cu:106-170)
+ *
+ * whose conventions this header keeps:
+ *   - `data` is a DEVICE pointer owned by the caller, n = 2^log_n elements, transformed IN PLACE,
+ *     natural order in and out;
+ *   - an element is cgbn_mem_t<256> (include/cgbn/cgbn_cuda.h:51-55): 8 little-endian u32 limbs,
+ *     32 bytes, canonical residue in [0, p), NOT in Montgomery form;
+ *   - `prime` and `omega` are 8-limb host values; `omega` is the multiplicative GENERATOR g and
+ *     the callee derives w_n = g^((p-1)/n) (big-num.cu:128-134, 292-296);
+ *   - X[k] = sum_j x[j] * w_n^(jk) mod p (CPU oracle NTT(), big-num.cu:37-55).
+ * What it drops: the bit-reversal pair list (`reverse`, `reverse_len`: no permutation pass exists
+ * here), the tuning knobs (B, G: chosen by the plan), the per-call twiddle table build
+ * (big-num.cu:298-309: tables live in the context), printing and asserts (status codes instead).
+ * What it adds: inverse transform (the reference's commented intent, big-num.cu:470-477),
+ * batches, streams, and the multi-GPU four-step pieces (SURVEY.md par. 8e).
+ *
+ * Threading: a context is bound to one device and is not re-entrant.  Calls are asynchronous
+ * on the given stream unless the name ends in _sync or takes host buffers.
+ * There is NO CPU fallback: every entry point fails with NTT256_ERR_CUDA if no sm_100 device
+ * can run it.
+ */
+#ifndef NTT256_H_
+#define NTT256_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ntt256_ctx ntt256_ctx;
+typedef void* ntt256_stream;  /* cudaStream_t; NULL = default stream */
+
+enum {
+  NTT256_OK = 0,
+  NTT256_ERR_ARG = 1,         /* null pointer, log_n out of range, bad field id */
+  NTT256_ERR_FIELD = 2,       /* p even, p >= 2^255, or 2^max_log_n does not divide p-1 */
+  NTT256_ERR_CUDA = 3,        /* CUDA runtime error; ntt256_last_cuda_error() has the text */
+  NTT256_ERR_NOMEM = 4,
+  NTT256_ERR_PLAN = 5         /* no pass plan found (internal) */
+};
+
+enum { NTT256_FIELD_BN254_FR = 0, NTT256_FIELD_BLS12_381_FR = 1 };
+
+/* Context for an arbitrary odd modulus p < 2^255 and generator g (both 8 LE u32 limbs), able to
+ * transform up to 2^max_log_n points.  Replaces the `prime`/`omega` by-value arguments of
+ * NTT_GZKP (big-num.cu:260-261) and the host twiddle precompute inside it (big-num.cu:278-309):
+ * tables are built once, on the device. */
+int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const uint32_t g[8], int max_log_n);
+/* Same for the two named fields of BASELINE.json (BN254 Fr with g = 5, BLS12-381 Fr with g = 7). */
+int ntt256_ctx_create_named(ntt256_ctx** out, int device, int field, int max_log_n);
+void ntt256_ctx_destroy(ntt256_ctx* ctx);
+
+/* Plan tuning (optional): tile_bits in [3,12] (shared-memory tile = 2^tile_bits elements),
+ * coalesce_bits in [0,6] (every global access run is >= 2^coalesce_bits elements).  Cached
+ * plans are discarded. */
+int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits);
+
+/* Forward NTT of 2^log_n points, in place on device memory, natural order in and out.
+ * == NTT_GZKP<8,256>(data, 1<<log_n, ..., prime, omega, B, G)  (big-num.cu:458). */
+int ntt256_forward(ntt256_ctx* ctx, void* d_data, int log_n, ntt256_stream stream);
+/* Inverse NTT including the 1/n scaling (big-num.cu:470-477: NTT with inv(root), times inv(length)). */
+int ntt256_inverse(ntt256_ctx* ctx, void* d_data, int log_n, ntt256_stream stream);
+/* `batch` independent transforms stored back to back (transform b at d_data + b * 32 * 2^log_n). */
+int ntt256_forward_batch(ntt256_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream);
+int ntt256_inverse_batch(ntt256_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream);
+
+/* Reference-like synchronous convenience: HOST buffer in, HOST buffer out (may alias), the
+ * library stages through its own device buffer: H2D, transform, D2H, synchronise.
+ * Mirrors main() of big-num.cu:424-460 (cudaMemcpy H2D, NTT_GZKP, cudaMemcpy D2H). */
+int ntt256_forward_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch);
+int ntt256_inverse_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch);
+
+/* Multi-GPU four-step pieces (SURVEY.md par. 8e).  One process per GPU; the all-to-all between
+ * the two calls is done by the caller (torch.distributed / NCCL, see ntt_b200/dist.py).
+ *   n = 2^log_n = R*C, R = 2^log_r rows, C = n/R columns, P = 2^log_p ranks.
+ *   Input shard of rank r: x[j1*C + j2] for j2 in [r*C/P, (r+1)*C/P), packed row-major R x (C/P).
+ *   step1: R-point column NTTs + twiddle w_n^(j2*k1), in place.
+ *   exchange: rank r sends rows k1 in [s*R/P, (s+1)*R/P) to rank s (contiguous chunks).
+ *   step2: on the received buffer laid out [src rank][k1 local][j2 local], C-point row NTTs;
+ *          output shard of rank r: X[k1 + R*k2] for k1 in block r, packed (R/P) x C. */
+int ntt256_fourstep_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                          ntt256_stream stream);
+int ntt256_fourstep_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                          ntt256_stream stream);
+
+/* Introspection (host only, no CUDA call): JSON description of the pass plan that
+ * ntt256_forward would run for 2^log_n points.  Returns the number of bytes needed
+ * (including the NUL); writes at most buf_len bytes. */
+size_t ntt256_plan_describe(int log_n, int max_log_n, int tile_bits, int coalesce_bits, char* buf, size_t buf_len);
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+unsigned long long ntt256_launch_count(const ntt256_ctx* ctx);
+
+const char* ntt256_strerror(int status);
+const char* ntt256_last_cuda_error(const ntt256_ctx* ctx);
+const char* ntt256_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTT256_H_ */

@@ -1,0 +1,185 @@
+"""Host-side mirror of the reference's 256-bit NTT entry points, over libntt256.so.
+
+The reference's boundary is a pair of C++ host drivers called from main()
+(/root/reference/src/big-num.cu:106-107, 260-261):
+
+    NTT_GPU_Naive<tpi,bits>(data_d, len, reverse_d, reverse_len, prime, omega)
+    NTT_GZKP<tpi,bits>(data_d, len, reverse_d, reverse_len, prime, omega, B, G)
+
+with `data_d` a device array of cgbn_mem_t<256> transformed in place (natural order in and
+out), `prime` / `omega` host values and `omega` the GENERATOR (the callee derives w_n).
+`NTT_GZKP` / `NTT_GPU_Naive` below keep those names and argument meanings (the bit-reversal
+list and the B/G knobs are accepted and ignored: this implementation has no permutation pass
+and picks its own tiling), and `Ntt256` is the context object the C ABI is built around.
+
+torch is used for device memory and streams only; all arithmetic happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .lib import Ntt256Error, lib as _load_lib
+
+FIELDS = {
+    "bn254_fr": (0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001, 5),
+    "bls12_381_fr": (0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001, 7),
+    "ref29": (469762049, 3),  # the only field the reference itself runs (big-num.cu:9-10)
+}
+
+
+def _limbs(v) -> np.ndarray:
+    if isinstance(v, (int, np.integer)):
+        v = int(v)
+        return np.array([(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
+    a = np.ascontiguousarray(v, dtype=np.uint32).reshape(-1)
+    if a.size != 8:
+        raise ValueError("a field element is 8 little-endian u32 limbs")
+    return a
+
+
+def _u32p(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+
+
+def _stream_handle(stream) -> Optional[int]:
+    if stream is None:
+        import torch
+
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, int):
+        return stream
+    return stream.cuda_stream
+
+
+def _device_ptr(data, n_elements: int) -> int:
+    """data: torch CUDA tensor holding n_elements * 32 contiguous bytes."""
+    if not getattr(data, "is_cuda", False):
+        raise TypeError("device entry points take a torch CUDA tensor (use *_host for numpy arrays)")
+    if not data.is_contiguous():
+        raise ValueError("data must be contiguous")
+    if data.numel() * data.element_size() != n_elements * 32:
+        raise ValueError(f"expected {n_elements} elements of 32 bytes, got {data.numel() * data.element_size()} bytes")
+    return data.data_ptr()
+
+
+class Ntt256:
+    """ntt256_ctx: field constants, device twiddle tables and plans for sizes up to 2^max_log_n."""
+
+    def __init__(self, field="bn254_fr", max_log_n: int = 24, device: int = 0, p=None, g=None):
+        L = _load_lib()
+        self._L = L
+        self._h = ctypes.c_void_p()
+        if p is None:
+            p, g = FIELDS[field]
+        self.p, self.g = int(p), int(g)
+        self.max_log_n = max_log_n
+        self.device = device
+        pl, gl = _limbs(self.p), _limbs(self.g)
+        rc = L.ntt256_ctx_create(ctypes.byref(self._h), device, _u32p(pl), _u32p(gl), max_log_n)
+        if rc:
+            raise Ntt256Error(rc)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.ntt256_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc:
+            raise Ntt256Error(rc, self._L.ntt256_last_cuda_error(self._h).decode())
+
+    def set_tuning(self, tile_bits: int, coalesce_bits: int):
+        self._check(self._L.ntt256_ctx_set_tuning(self._h, tile_bits, coalesce_bits))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.ntt256_launch_count(self._h))
+
+    # ---- device entry points (in place, asynchronous on `stream`)
+    def forward(self, data, log_n: int, batch: int = 1, stream=None):
+        ptr = _device_ptr(data, batch << log_n)
+        self._check(self._L.ntt256_forward_batch(self._h, ptr, log_n, batch, _stream_handle(stream)))
+        return data
+
+    def inverse(self, data, log_n: int, batch: int = 1, stream=None):
+        ptr = _device_ptr(data, batch << log_n)
+        self._check(self._L.ntt256_inverse_batch(self._h, ptr, log_n, batch, _stream_handle(stream)))
+        return data
+
+    def fourstep_step1(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        ptr = _device_ptr(shard, 1 << (log_n - log_p))
+        self._check(self._L.ntt256_fourstep_step1(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))
+        return shard
+
+    def fourstep_step2(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        ptr = _device_ptr(shard, 1 << (log_n - log_p))
+        self._check(self._L.ntt256_fourstep_step2(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))
+        return shard
+
+    # ---- host entry points (numpy in, numpy out, synchronous; H2D + transform + D2H)
+    def forward_host(self, x: np.ndarray, log_n: int, batch: int = 1, out: Optional[np.ndarray] = None):
+        return self._host(self._L.ntt256_forward_host, x, log_n, batch, out)
+
+    def inverse_host(self, x: np.ndarray, log_n: int, batch: int = 1, out: Optional[np.ndarray] = None):
+        return self._host(self._L.ntt256_inverse_host, x, log_n, batch, out)
+
+    def _host(self, fn, x, log_n, batch, out):
+        x = np.ascontiguousarray(x, dtype=np.uint32)
+        if x.size != (batch << log_n) * 8:
+            raise ValueError("host array must hold batch * 2^log_n elements of 8 u32 limbs")
+        if out is None:
+            out = np.empty_like(x)
+        self._check(fn(self._h, x.ctypes.data, out.ctypes.data, log_n, batch))
+        return out
+
+
+_CTX_CACHE: dict = {}
+
+
+def _cached_ctx(device: int, p: int, g: int, log_n: int) -> Ntt256:
+    two_adicity = ((p - 1) & -(p - 1)).bit_length() - 1
+    max_log_n = min(max(log_n, 12), two_adicity, 32)
+    key = (device, p, g)
+    ctx = _CTX_CACHE.get(key)
+    if ctx is None or ctx.max_log_n < log_n:
+        if ctx is not None:
+            ctx.close()
+            max_log_n = min(max(max_log_n, ctx.max_log_n), two_adicity)
+        ctx = Ntt256(max_log_n=max_log_n, device=device, p=p, g=g)
+        _CTX_CACHE[key] = ctx
+    return ctx
+
+
+def _from_limbs(v) -> int:
+    if isinstance(v, (int, np.integer)):
+        return int(v)
+    return sum(int(l) << (32 * i) for i, l in enumerate(np.asarray(v).reshape(-1)))
+
+
+def NTT_GZKP(data, length: int, reverse=None, reverse_len: int = 0, prime=None, omega=None, B: int = 0, G: int = 0,
+             stream=None):
+    """Drop-in for NTT_GZKP<8,256> (big-num.cu:260-353): in-place forward NTT of `length` points
+    on device memory; `prime`, `omega` (= generator) are ints or 8-limb arrays.  `reverse`,
+    `reverse_len`, `B`, `G` are accepted for signature compatibility and ignored.  Unlike the
+    reference it does not synchronise or print; errors raise Ntt256Error."""
+    if length <= 0 or length & (length - 1):
+        raise ValueError("length must be a power of two (the reference asserts it, big-num.cu:385)")
+    log_n = length.bit_length() - 1
+    p, g = _from_limbs(prime), _from_limbs(omega)
+    ctx = _cached_ctx(data.device.index or 0, p, g, log_n)
+    return ctx.forward(data, log_n, 1, stream)
+
+
+def NTT_GPU_Naive(data, length: int, reverse=None, reverse_len: int = 0, prime=None, omega=None, stream=None):
+    """Drop-in for NTT_GPU_Naive<8,256> (big-num.cu:106-170): same contract and same results as
+    NTT_GZKP (the reference checks both against the same CPU output, big-num.cu:439-467)."""
+    return NTT_GZKP(data, length, reverse, reverse_len, prime, omega, 0, 0, stream)

@@ -1,0 +1,439 @@
+// C ABI of libntt256.so (include/ntt256.h): context, device twiddle tables, plan cache and the
+// launch sequences.  Host-side counterpart of the reference drivers NTT_GPU_Naive / NTT_GZKP
+// (/root/reference/src/big-num.cu:106-170, 260-353) -- minus their per-call table build,
+// bit-reversal list and printing.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <algorithm>
+#include <new>
+#include <tuple>
+#include <string>
+#include <vector>
+
+#include "../../include/ntt256.h"
+#include "hostfield.h"
+#include "ntt_kernels.cuh"
+#include "plan.h"
+
+using namespace ntt256;
+
+namespace {
+
+constexpr int kHiBitsMax = 18;  // w^(i<<lo) table: 2^18 entries = 8 MiB, stays in L2
+constexpr int kLocBitsMax = 12;
+
+struct PlanKey {
+  int kind;  // 0 = whole transform, 1 = four-step step 1, 2 = four-step step 2
+  int log_n, log_r, log_p, rank;
+  bool operator<(const PlanKey& o) const {
+    return std::tie(kind, log_n, log_r, log_p, rank) < std::tie(o.kind, o.log_n, o.log_r, o.log_p, o.rank);
+  }
+};
+
+}  // namespace
+
+struct ntt256_ctx {
+  int device = 0;
+  int max_log_n = 0;
+  HostField hf;
+  FieldParams fp;
+  U256 g_mont;       // generator, Montgomery form
+  U256 wN, wN_inv;   // w_{2^max_log_n} and its inverse, Montgomery form
+  uint4* om_hi = nullptr;
+  uint4* om_lo = nullptr;
+  uint4* loc = nullptr;
+  int hi_bits = 0, lo_bits = 0, loc_bits = 0;
+  u32 c8[2][3][8];   // [direction][k-1] = w_8^(+-k)
+  u32 w4[2][8];
+  int tile_bits = 10;
+  int coalesce_bits = 2;
+  std::map<PlanKey, Plan> plans;
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  unsigned long long launches = 0;
+  std::string last_err;
+};
+
+namespace {
+
+#define CTX_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) {                             \
+      ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+      return NTT256_ERR_CUDA;                            \
+    }                                                    \
+  } while (0)
+
+U256 root_of_unity(const HostField& hf, const U256& g_mont, int log_n) {
+  U256 pm1, e;
+  u256_sub(pm1, hf.p, u256_small(1));
+  e = u256_shr(pm1, log_n);  // (p-1)/n, exact: checked at context creation
+  return hf.pow(g_mont, e);
+}
+
+U256 pow2k(const HostField& hf, U256 b, int k) {  // b^(2^k)
+  for (int i = 0; i < k; ++i) b = hf.mul(b, b);
+  return b;
+}
+
+void to_u32(const U256& a, u32 out[8]) { u256_to_limbs(a, out); }
+
+int build_power_table(ntt256_ctx* ctx, uint4** out, const U256& base_mont, int bits) {
+  const unsigned long long count = 1ull << bits;
+  CTX_CUDA(cudaMalloc((void**)out, count * 32));
+  std::vector<u32> pw(8 * 64, 0);
+  U256 b = base_mont;
+  for (int k = 0; k < std::max(bits, 1); ++k) {
+    to_u32(b, &pw[8 * k]);
+    b = ctx->hf.mul(b, b);
+  }
+  uint4* d_pw = nullptr;
+  CTX_CUDA(cudaMalloc((void**)&d_pw, pw.size() * 4));
+  CTX_CUDA(cudaMemcpy(d_pw, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));
+  Fe one;
+  to_u32(ctx->hf.one, one.v);
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((count + threads - 1) / threads);
+  twiddle_powers_kernel<<<blocks, threads>>>(*out, d_pw, bits, 0ull, count, ctx->fp, one);
+  ++ctx->launches;
+  CTX_CUDA(cudaGetLastError());
+  CTX_CUDA(cudaDeviceSynchronize());
+  CTX_CUDA(cudaFree(d_pw));
+  return NTT256_OK;
+}
+
+int get_plan(ntt256_ctx* ctx, const PlanKey& key, const Plan** out) {
+  auto it = ctx->plans.find(key);
+  if (it == ctx->plans.end()) {
+    PlanRequest req;
+    req.tile_bits = ctx->tile_bits;
+    req.coalesce_bits = ctx->coalesce_bits;
+    req.max_log_n = ctx->max_log_n;
+    req.log_n = key.log_n;
+    if (key.kind != 0) {
+      const int L = key.log_n, lr = key.log_r, lp = key.log_p, lc = L - lr;
+      const int nloc = L - lp;
+      req.total_log_n = L;
+      req.start.resize(nloc);
+      req.target.resize(nloc);
+      if (key.kind == 1) {
+        // local index = j1 * (C/P) + j2_local ; rank = top lp bits of j2
+        for (int p = 0; p < lc - lp; ++p) req.start[p] = p, req.target[p] = p;
+        for (int i = 0; i < lr; ++i) {
+          req.start[lc - lp + i] = lc + i;
+          req.target[lc - lp + i] = 64 + i;  // k1 natural above j2_local
+        }
+        req.time_hi = L - 1;
+        req.time_lo = lc;
+        req.jlow_const = (uint32_t)key.rank << (lc - lp);
+      } else {
+        // received layout [src rank][k1 local][j2 local]
+        for (int p = 0; p < lc - lp; ++p) req.start[p] = p;
+        for (int c = 0; c < lr - lp; ++c) req.start[lc - lp + c] = 64 + c;
+        for (int i = 0; i < lp; ++i) req.start[lc - lp + lr - lp + i] = lc - lp + i;
+        // output [k1 local][k2]: k2 bit i = k_{lr+i}
+        for (int i = 0; i < lc; ++i) req.target[i] = 64 + lr + i;
+        for (int c = 0; c < lr - lp; ++c) req.target[lc + c] = 64 + c;
+        req.time_hi = lc - 1;
+        req.time_lo = 0;
+        req.jlow_const = 0;
+      }
+    }
+    Plan plan;
+    if (!make_plan(req, &plan)) return NTT256_ERR_PLAN;
+    it = ctx->plans.emplace(key, plan).first;
+  }
+  *out = &it->second;
+  return NTT256_OK;
+}
+
+int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long batch_stride, int batch, bool inverse,
+             int scale_log_n, cudaStream_t stream) {
+  PassArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.f = ctx->fp;
+  A.om_hi = ctx->om_hi;
+  A.om_lo = ctx->om_lo;
+  A.loc = ctx->loc;
+  A.hi_bits = ctx->hi_bits;
+  A.lo_bits = ctx->lo_bits;
+  A.loc_bits = ctx->loc_bits;
+  A.inverse = inverse ? 1 : 0;
+  std::memcpy(A.c8, ctx->c8[inverse ? 1 : 0], sizeof(A.c8));
+  A.batch_stride = batch_stride;
+  if (scale_log_n >= 0) {
+    U256 nm = ctx->hf.to_mont(u256_small(1ull << scale_log_n));
+    to_u32(ctx->hf.inv(nm), A.scale);
+  }
+  for (size_t i = 0; i < plan.passes.size(); ++i) {
+    A.pd = plan.passes[i];
+    if (scale_log_n >= 0 && i + 1 == plan.passes.size()) A.pd.scale_out = 1;
+    const int T = A.pd.T;
+    const unsigned threads = 1u << (T - 3);
+    const size_t smem = (size_t)32 << T;
+    const unsigned long long nblk = 1ull << A.pd.nblk_bits;
+    if (nblk > 0x7fffffffull || batch > 65535) return NTT256_ERR_ARG;
+    dim3 grid((unsigned)nblk, (unsigned)batch, 1);
+    ntt_pass_kernel<<<grid, threads, smem, stream>>>((uint4*)d_data, A);
+    ++ctx->launches;
+    CTX_CUDA(cudaGetLastError());
+  }
+  return NTT256_OK;
+}
+
+int run_tiny(ntt256_ctx* ctx, void* d_data, int log_n, unsigned long long batch, bool inverse, cudaStream_t stream) {
+  if (log_n == 0) return NTT256_OK;
+  TinyArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.f = ctx->fp;
+  A.log_n = log_n;
+  std::memcpy(A.w4, ctx->w4[inverse ? 1 : 0], sizeof(A.w4));
+  A.do_scale = inverse ? 1 : 0;
+  if (inverse) {
+    U256 nm = ctx->hf.to_mont(u256_small(1ull << log_n));
+    to_u32(ctx->hf.inv(nm), A.scale);
+  }
+  A.batch = batch;
+  const int threads = 128;
+  ntt_tiny_kernel<<<(unsigned)((batch + threads - 1) / threads), threads, 0, stream>>>((uint4*)d_data, A);
+  ++ctx->launches;
+  CTX_CUDA(cudaGetLastError());
+  return NTT256_OK;
+}
+
+int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse, cudaStream_t stream) {
+  if (!ctx || !d_data || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  if (log_n < 3) return run_tiny(ctx, d_data, log_n, (unsigned long long)batch, inverse, stream);
+  const Plan* plan = nullptr;
+  int rc = get_plan(ctx, PlanKey{0, log_n, 0, 0, 0}, &plan);
+  if (rc) return rc;
+  // batches larger than one grid dimension are issued in slices
+  const int kSlice = 65535;
+  for (int b0 = 0; b0 < batch; b0 += kSlice) {
+    const int nb = std::min(kSlice, batch - b0);
+    char* p = (char*)d_data + ((size_t)b0 << log_n) * 32;
+    rc = run_plan(ctx, *plan, p, 1ull << log_n, nb, inverse, inverse ? log_n : -1, stream);
+    if (rc) return rc;
+  }
+  return NTT256_OK;
+}
+
+int transform_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch, bool inverse) {
+  if (!ctx || !h_in || !h_out || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = ((size_t)batch << log_n) * 32;
+  if (bytes > ctx->stage_bytes) {
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr;
+    ctx->stage_bytes = 0;
+    CTX_CUDA(cudaMalloc(&ctx->d_stage, bytes));
+    ctx->stage_bytes = bytes;
+  }
+  CTX_CUDA(cudaMemcpyAsync(ctx->d_stage, h_in, bytes, cudaMemcpyHostToDevice, 0));
+  int rc = transform(ctx, ctx->d_stage, log_n, batch, inverse, 0);
+  if (rc) return rc;
+  CTX_CUDA(cudaMemcpyAsync(h_out, ctx->d_stage, bytes, cudaMemcpyDeviceToHost, 0));
+  CTX_CUDA(cudaStreamSynchronize(0));
+  return NTT256_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const uint32_t g[8], int max_log_n) {
+  if (!out || !p || !g || max_log_n < 1 || max_log_n > 32) return NTT256_ERR_ARG;
+  *out = nullptr;
+  U256 P = u256_from_limbs(p), G = u256_from_limbs(g);
+  if (!(P.w[0] & 1) || u256_bitlen(P) > 255 || u256_bitlen(P) < 2) return NTT256_ERR_FIELD;
+  if (u256_is_zero(G) || u256_cmp(G, P) >= 0) return NTT256_ERR_FIELD;
+  U256 pm1;
+  u256_sub(pm1, P, u256_small(1));
+  for (int i = 0; i < max_log_n; ++i)
+    if (u256_bit(pm1, i)) return NTT256_ERR_FIELD;
+  ntt256_ctx* ctx = new (std::nothrow) ntt256_ctx();
+  if (!ctx) return NTT256_ERR_NOMEM;
+  ctx->device = device;
+  ctx->max_log_n = max_log_n;
+  ctx->hf.init(P);
+  std::memset(&ctx->fp, 0, sizeof(ctx->fp));
+  u256_to_limbs(P, ctx->fp.p);
+  U256 P2;
+  u256_add(P2, P, P);
+  u256_to_limbs(P2, ctx->fp.p2);
+  ctx->fp.np0 = (u32)ctx->hf.np0;
+  ctx->g_mont = ctx->hf.to_mont(G);
+  ctx->wN = root_of_unity(ctx->hf, ctx->g_mont, max_log_n);
+  ctx->wN_inv = ctx->hf.inv(ctx->wN);
+  // w_N must have exact order N (g is a generator / non-residue): w_N^(N/2) == -1
+  {
+    U256 h = pow2k(ctx->hf, ctx->wN, max_log_n - 1), m1;
+    m1 = ctx->hf.sub(u256_small(0), ctx->hf.one);
+    if (u256_cmp(h, m1) != 0) {
+      delete ctx;
+      return NTT256_ERR_FIELD;
+    }
+  }
+  ctx->hi_bits = std::min(max_log_n, kHiBitsMax);
+  ctx->lo_bits = max_log_n - ctx->hi_bits;
+  ctx->loc_bits = std::min(max_log_n, kLocBitsMax);
+  std::memset(ctx->c8, 0, sizeof(ctx->c8));
+  std::memset(ctx->w4, 0, sizeof(ctx->w4));
+  if (max_log_n >= 3) {
+    U256 w8 = pow2k(ctx->hf, ctx->wN, max_log_n - 3);
+    U256 w8i = pow2k(ctx->hf, ctx->wN_inv, max_log_n - 3);
+    U256 a = w8, b = w8i;
+    for (int k = 0; k < 3; ++k) {
+      to_u32(a, ctx->c8[0][k]);
+      to_u32(b, ctx->c8[1][k]);
+      a = ctx->hf.mul(a, w8);
+      b = ctx->hf.mul(b, w8i);
+    }
+  }
+  if (max_log_n >= 2) {
+    to_u32(pow2k(ctx->hf, ctx->wN, max_log_n - 2), ctx->w4[0]);
+    to_u32(pow2k(ctx->hf, ctx->wN_inv, max_log_n - 2), ctx->w4[1]);
+    if (max_log_n < 3) {  // radix-4 rounds use c8[1] = w_4
+      std::memcpy(ctx->c8[0][1], ctx->w4[0], 32);
+      std::memcpy(ctx->c8[1][1], ctx->w4[1], 32);
+    }
+  }
+  int rc = NTT256_OK;
+  auto fail = [&](int code) {
+    ntt256_ctx_destroy(ctx);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTT256_ERR_CUDA);
+  if (cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMaxTileBits) !=
+      cudaSuccess)
+    return fail(NTT256_ERR_CUDA);
+  rc = build_power_table(ctx, &ctx->om_hi, pow2k(ctx->hf, ctx->wN, ctx->lo_bits), ctx->hi_bits);
+  if (rc) return fail(rc);
+  rc = build_power_table(ctx, &ctx->om_lo, ctx->wN, ctx->lo_bits);
+  if (rc) return fail(rc);
+  rc = build_power_table(ctx, &ctx->loc, pow2k(ctx->hf, ctx->wN, max_log_n - ctx->loc_bits), ctx->loc_bits);
+  if (rc) return fail(rc);
+  *out = ctx;
+  return NTT256_OK;
+}
+
+int ntt256_ctx_create_named(ntt256_ctx** out, int device, int field, int max_log_n) {
+  static const uint32_t bn254_p[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                      0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+  static const uint32_t bls_p[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                    0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+  uint32_t g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (field == NTT256_FIELD_BN254_FR) {
+    g[0] = 5;
+    return ntt256_ctx_create(out, device, bn254_p, g, max_log_n);
+  }
+  if (field == NTT256_FIELD_BLS12_381_FR) {
+    g[0] = 7;
+    return ntt256_ctx_create(out, device, bls_p, g, max_log_n);
+  }
+  return NTT256_ERR_ARG;
+}
+
+void ntt256_ctx_destroy(ntt256_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->om_hi) cudaFree(ctx->om_hi);
+  if (ctx->om_lo) cudaFree(ctx->om_lo);
+  if (ctx->loc) cudaFree(ctx->loc);
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  delete ctx;
+}
+
+int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits) {
+  if (!ctx || tile_bits < 3 || tile_bits > kMaxTileBits || coalesce_bits < 0 || coalesce_bits > 6 ||
+      coalesce_bits > tile_bits)
+    return NTT256_ERR_ARG;
+  ctx->tile_bits = tile_bits;
+  ctx->coalesce_bits = coalesce_bits;
+  ctx->plans.clear();
+  return NTT256_OK;
+}
+
+int ntt256_forward(ntt256_ctx* ctx, void* d_data, int log_n, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, 1, false, (cudaStream_t)stream);
+}
+int ntt256_inverse(ntt256_ctx* ctx, void* d_data, int log_n, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, 1, true, (cudaStream_t)stream);
+}
+int ntt256_forward_batch(ntt256_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, batch, false, (cudaStream_t)stream);
+}
+int ntt256_inverse_batch(ntt256_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, batch, true, (cudaStream_t)stream);
+}
+int ntt256_forward_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch) {
+  return transform_host(ctx, h_in, h_out, log_n, batch, false);
+}
+int ntt256_inverse_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch) {
+  return transform_host(ctx, h_in, h_out, log_n, batch, true);
+}
+
+static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                    cudaStream_t stream) {
+  if (!ctx || !d_shard || log_n > ctx->max_log_n || log_p < 0 || log_r < log_p || log_n - log_r < log_p ||
+      rank < 0 || rank >= (1 << log_p) || log_n - log_p < 3)
+    return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  const Plan* plan = nullptr;
+  // step 2 does not depend on the rank (no foreign time bits remain)
+  int rc = get_plan(ctx, PlanKey{kind, log_n, log_r, log_p, kind == 1 ? rank : 0}, &plan);
+  if (rc) return rc;
+  return run_plan(ctx, *plan, d_shard, 0, 1, false, -1, stream);
+}
+
+int ntt256_fourstep_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                          ntt256_stream stream) {
+  return fourstep(ctx, 1, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream);
+}
+int ntt256_fourstep_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                          ntt256_stream stream) {
+  return fourstep(ctx, 2, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream);
+}
+
+size_t ntt256_plan_describe(int log_n, int max_log_n, int tile_bits, int coalesce_bits, char* buf, size_t buf_len) {
+  PlanRequest req;
+  req.log_n = log_n;
+  req.max_log_n = max_log_n;
+  req.tile_bits = tile_bits;
+  req.coalesce_bits = coalesce_bits;
+  Plan plan;
+  std::string s;
+  if (log_n < 3 || !make_plan(req, &plan))
+    s = "{\"error\": \"no plan\"}";
+  else
+    s = plan.describe();
+  if (buf && buf_len) {
+    size_t n = std::min(buf_len - 1, s.size());
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return s.size() + 1;
+}
+
+unsigned long long ntt256_launch_count(const ntt256_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+const char* ntt256_strerror(int status) {
+  switch (status) {
+    case NTT256_OK: return "ok";
+    case NTT256_ERR_ARG: return "invalid argument";
+    case NTT256_ERR_FIELD: return "unsupported field (need odd p < 2^255, 2^max_log_n | p-1, g of full 2-power order)";
+    case NTT256_ERR_CUDA: return "CUDA error";
+    case NTT256_ERR_NOMEM: return "out of memory";
+    case NTT256_ERR_PLAN: return "no pass plan";
+    default: return "unknown status";
+  }
+}
+const char* ntt256_last_cuda_error(const ntt256_ctx* ctx) { return ctx ? ctx->last_err.c_str() : ""; }
+const char* ntt256_version(void) { return "ntt256-b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

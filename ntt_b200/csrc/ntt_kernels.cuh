@@ -1,0 +1,330 @@
+// Device kernels of the self-sorting in-place 256-bit NTT (sm_100a).
+//
+//   ntt_pass_kernel   one pass of the plan (plan.h): a CTA owns a tile of 2^T elements picked
+//                     by T index bits, each thread keeps 8 elements in registers, runs up to
+//                     three DIF stages per register round, exchanges through a limb-major,
+//                     XOR-swizzled shared-memory tile between rounds, multiplies by the pass
+//                     twiddle and stores the tile back with its index bits permuted.
+//                     Replaces rearrange + naive + GZKP of /root/reference/src/big-num.cu:57-258.
+//   ntt_tiny_kernel   transforms of 2 or 4 points (one thread per transform).
+//   twiddle_powers_kernel   builds w^i tables on the device (the reference builds an n-entry
+//                     table serially on the host at every call, big-num.cu:298-309).
+//
+// Global memory is touched with one 256-bit LDG/STG per element (LDG.E.ENL2.256); a warp reads
+// runs of >= 2^g consecutive elements (g = plan coalesce_bits).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "field.cuh"
+#include "plan.h"
+
+namespace ntt256 {
+
+struct PassArgs {
+  FieldParams f;
+  PassDesc pd;
+  const uint4* om_hi;  // w_N^(i << lo_bits), i < 2^hi_bits, Montgomery form, canonical
+  const uint4* om_lo;  // w_N^i, i < 2^lo_bits
+  const uint4* loc;    // w_{2^loc_bits}^i, i < 2^loc_bits (round twiddles; loc_bits = min(12, max_log_n))
+  int hi_bits, lo_bits;  // hi_bits + lo_bits = max_log_n
+  int loc_bits;
+  int inverse;         // 1: exponents are negated (w^-1 tables are the same tables read backwards)
+  u32 c8[3][8];        // w_8^1, w_8^2, w_8^3 (or their inverses), Montgomery form
+  u32 scale[8];        // 1/n in Montgomery form (used when pd.scale_out)
+  unsigned long long batch_stride;  // elements between consecutive transforms of a batch
+};
+
+// ---------------------------------------------------------------- element I/O
+NTT_DEV void ld_global_256(u32* v, const uint4* p) {
+  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+NTT_DEV void st_global_256(uint4* p, const u32* v) {
+  asm volatile("st.global.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "l"(p)
+               : "memory");
+}
+// read-only twiddle tables: non-coherent path, two 128-bit loads
+NTT_DEV void ld_table(u32* v, const uint4* tab, u32 idx) {
+  const uint4 a = __ldg(tab + 2 * (size_t)idx);
+  const uint4 b = __ldg(tab + 2 * (size_t)idx + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// x <- w * x  (w canonical Montgomery-form constant, x lazy)
+NTT_DEV void mul_by(u32* x, const u32* w, const FieldParams& f) {
+  u32 r[8];
+  mont_mul(r, w, x, f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = r[k];
+}
+
+// DIF butterfly: (a, b) <- (a + b, a - b)
+NTT_DEV void bfly(u32* a, u32* b, const FieldParams& f) {
+  u32 s[8], d[8];
+  add_lazy(s, a, b, f);
+  sub_lazy(d, a, b, f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    a[k] = s[k];
+    b[k] = d[k];
+  }
+}
+
+// shared-memory tile: limb-major words, element index swizzled so that any 5 lane bits that
+// are distinct mod 5 hit 32 distinct banks.
+NTT_DEV u32 swz(u32 l) { return l ^ ((l >> 5) & 31u) ^ ((l >> 10) & 31u); }
+
+// bit deposit: bit i of v goes to position pos[i]
+NTT_DEV u32 deposit32(u32 v, const int8_t* pos, int n) {
+  u32 r = 0;
+  for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << pos[i];
+  return r;
+}
+NTT_DEV unsigned long long deposit64(unsigned long long v, const int8_t* pos, int n) {
+  unsigned long long r = 0;
+  for (int i = 0; i < n; ++i) r |= ((v >> i) & 1ull) << pos[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(512, 1)
+ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
+  extern __shared__ u32 smem[];
+  const PassDesc& pd = A.pd;
+  const FieldParams& f = A.f;
+  const int T = pd.T;
+  const int d = pd.d;
+  const u32 tid = threadIdx.x;
+  const u32 tile_words = 1u << T;
+
+  // ---- block-level index pieces (uniform)
+  const unsigned long long blk = blockIdx.x;
+  unsigned long long base = deposit64(blk, pd.blk_pos, pd.nblk_bits);
+  u32 jlow_blk = pd.jlow_const;
+  for (int i = 0; i < pd.nblk_bits; ++i) jlow_blk += (u32)((blk >> i) & 1ull) * pd.wt_blk[i];
+  base += (unsigned long long)blockIdx.y * A.batch_stride;
+  uint4* gbase = data + 2 * base;
+
+  u32 x[8][8];
+
+  for (int r = 0; r < pd.nrounds; ++r) {
+    const int sb = pd.round_sb[r];
+    const int nb = pd.round_nb[r];
+    const u32 lam0 = deposit32(tid, pd.tmap[r], T - 3);
+    const bool first = (r == 0);
+    const bool last = (r == pd.nrounds - 1);
+
+    // ---- fetch the 8 elements of this thread
+    if (first) {
+      const u32 g0 = deposit32(lam0, pd.in_pos, T);
+      const u32 s0 = 1u << pd.in_pos[sb], s1 = 1u << pd.in_pos[sb + 1], s2 = 1u << pd.in_pos[sb + 2];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const u32 off = g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+        ld_global_256(x[u], gbase + 2 * (size_t)off);
+      }
+    } else {
+      const u32 w0 = swz(lam0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const u32 w = w0 ^ swz((u32)u << sb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[u][k] = smem[k * tile_words + w];
+      }
+    }
+
+    // ---- butterflies on the top nb bits of the 3-bit group
+    if (nb == 3) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        bfly(x[u], x[u + 4], f);
+        if (u) mul_by(x[u + 4], A.c8[u - 1], f);
+      }
+#pragma unroll
+      for (int h = 0; h < 8; h += 4)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          bfly(x[h + u], x[h + u + 2], f);
+          if (u) mul_by(x[h + u + 2], A.c8[1], f);
+        }
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) bfly(x[u], x[u + 1], f);
+    } else if (nb == 2) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        bfly(x[u], x[u + 4], f);
+        if (u & 2) mul_by(x[u + 4], A.c8[1], f);
+      }
+#pragma unroll
+      for (int h = 0; h < 8; h += 4)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) bfly(x[h + u], x[h + u + 2], f);
+    } else if (nb == 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) bfly(x[u], x[u + 4], f);
+    }
+
+    if (!last) {
+      // ---- local twiddle w_{2^m}^(tau_lo * v): m = process bits from this group's top down
+      const int lowp = T - d;            // lowest process bit
+      const int pb = sb + 3 - nb;        // lowest bit butterflied in this round
+      const int m = sb + 3 - lowp;
+      const int sh = A.loc_bits - m;
+      const u32 tl_mask = (1u << (pb - lowp)) - 1u;
+      const u32 tl0 = (lam0 >> lowp) & tl_mask;
+      const int ush = sb - lowp;         // >= 0 here (only the last round can dip below)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        // v = bit-reversed processed bits of u; tau_lo includes the group's unprocessed bits
+        u32 v, rest;
+        if (nb == 3) { v = ((u & 4) >> 2) | (u & 2) | ((u & 1) << 2); rest = 0; }
+        else if (nb == 2) { v = ((u >> 2) & 1) | (((u >> 1) & 1) << 1); rest = u & 1; }
+        else { v = (u >> 2) & 1; rest = u & 3; }
+        if (nb == 3 ? (u != 0) : (nb == 2 ? ((u >> 1) != 0) : ((u >> 2) != 0))) {
+          const u32 tl = (tl0 | (rest << ush)) & tl_mask;
+          u32 e = (tl * v) << sh;
+          if (A.inverse) e = (0u - e);
+          e &= (1u << A.loc_bits) - 1u;
+          u32 w[8];
+          ld_table(w, A.loc, e);
+          mul_by(x[u], w, f);
+        }
+      }
+      // ---- exchange
+      const u32 w0 = swz(lam0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const u32 w = w0 ^ swz((u32)u << sb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) smem[k * tile_words + w] = x[u][k];
+      }
+      __syncthreads();
+    } else {
+      // ---- pass twiddle, scale, canonical form, store
+      const int lowp = T - d;
+      if (pd.has_tw) {
+        u32 jl0 = jlow_blk;
+        for (int i = 0; i < lowp; ++i) jl0 += ((lam0 >> i) & 1u) * pd.wt_loc[i];
+        const u32 gw0 = (sb + 0 < lowp) ? pd.wt_loc[sb + 0] : 0u;
+        const u32 gw1 = (sb + 1 < lowp) ? pd.wt_loc[sb + 1] : 0u;
+        const u32 gw2 = (sb + 2 < lowp) ? pd.wt_loc[sb + 2] : 0u;
+        const u32 nmask = (A.hi_bits + A.lo_bits >= 32) ? 0xffffffffu : ((1u << (A.hi_bits + A.lo_bits)) - 1u);
+        const u32 lomask = (1u << A.lo_bits) - 1u;
+        const bool two = pd.tw_lshift < A.lo_bits;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const u32 lam = lam0 | ((u32)u << sb);
+          const u32 khi = d ? (__brev(lam >> lowp) >> (32 - d)) : 0u;
+          const u32 jl = jl0 + ((u & 1) ? gw0 : 0u) + ((u & 2) ? gw1 : 0u) + ((u & 4) ? gw2 : 0u);
+          u32 e = (jl * khi) << pd.tw_lshift;
+          if (A.inverse) e = (0u - e);
+          e &= nmask;
+          u32 w[8];
+          ld_table(w, A.om_hi, e >> A.lo_bits);
+          mul_by(x[u], w, f);
+          if (two) {
+            ld_table(w, A.om_lo, e & lomask);
+            mul_by(x[u], w, f);
+          }
+        }
+      }
+      if (pd.scale_out) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mul_by(x[u], A.scale, f);
+      }
+      if (pd.is_final) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) canonicalize(x[u], f);
+      }
+      // a single-round pass loads and stores global memory in the same round: every thread of
+      // the CTA must have loaded before any permuted store lands on another thread's input
+      if (first) __syncthreads();
+      const u32 g0 = deposit32(lam0, pd.out_pos, T);
+      const u32 s0 = 1u << pd.out_pos[sb], s1 = 1u << pd.out_pos[sb + 1], s2 = 1u << pd.out_pos[sb + 2];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const u32 off = g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+        st_global_256(gbase + 2 * (size_t)off, x[u]);
+      }
+    }
+  }
+}
+
+// Transforms of 2 or 4 points: one thread per transform, exact radix-2 DIF + bit reversal.
+struct TinyArgs {
+  FieldParams f;
+  int log_n;
+  u32 w4[8];      // w_4 (or its inverse), Montgomery form
+  u32 scale[8];   // 1/n Montgomery form
+  int do_scale;
+  unsigned long long batch;
+};
+
+__global__ void ntt_tiny_kernel(uint4* __restrict__ data, const __grid_constant__ TinyArgs A) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.batch) return;
+  const FieldParams& f = A.f;
+  const int n = 1 << A.log_n;
+  uint4* p = data + 2 * t * n;
+  u32 x[4][8];
+  for (int i = 0; i < n; ++i) ld_global_256(x[i], p + 2 * i);
+  if (A.log_n == 1) {
+    bfly(x[0], x[1], f);
+  } else if (A.log_n == 2) {
+    bfly(x[0], x[2], f);
+    bfly(x[1], x[3], f);
+    mul_by(x[3], A.w4, f);
+    bfly(x[0], x[1], f);
+    bfly(x[2], x[3], f);
+    // bit reversal of a 4-point DIF: swap positions 1 and 2
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      u32 tmp = x[1][k];
+      x[1][k] = x[2][k];
+      x[2][k] = tmp;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    if (A.do_scale) mul_by(x[i], A.scale, f);
+    canonicalize(x[i], f);
+    st_global_256(p + 2 * i, x[i]);
+  }
+}
+
+// out[i] = prod over set bits k of i of pw[k]   (pw[k] = w^(2^k) in Montgomery form), i.e. w^i.
+// `first` offsets the exponent: out[i] = w^(first + i).
+__global__ void twiddle_powers_kernel(uint4* __restrict__ out, const uint4* __restrict__ pw, int nbits,
+                                      unsigned long long first, unsigned long long count,
+                                      const __grid_constant__ FieldParams f, const __grid_constant__ Fe one) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const unsigned long long e = first + i;
+  u32 acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = one.v[k];
+  for (int b = 0; b < nbits; ++b) {
+    if ((e >> b) & 1ull) {
+      u32 w[8];
+      ld_table(w, pw, (u32)b);
+      mul_by(acc, w, f);
+    }
+  }
+  canonicalize(acc, f);
+  st_global_256(out + 2 * i, acc);
+}
+
+// out[i] = c * in[i]  (c Montgomery-form constant): scaled copies of small tables.
+__global__ void table_scale_kernel(uint4* __restrict__ out, const uint4* __restrict__ in, unsigned long long count,
+                                   const __grid_constant__ FieldParams f, const __grid_constant__ Fe c) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u32 x[8];
+  ld_global_256(x, in + 2 * i);
+  mul_by(x, c.v, f);
+  canonicalize(x, f);
+  st_global_256(out + 2 * i, x);
+}
+
+}  // namespace ntt256

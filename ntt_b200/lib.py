@@ -1,0 +1,77 @@
+"""ctypes binding of libntt256.so (include/ntt256.h).  The CUDA library is the product: there
+is no CPU or PyTorch fallback -- a missing or unloadable library raises at import of this
+module's `lib()`."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libntt256.so")
+_LIB = None
+
+OK, ERR_ARG, ERR_FIELD, ERR_CUDA, ERR_NOMEM, ERR_PLAN = range(6)
+FIELD_BN254_FR, FIELD_BLS12_381_FR = 0, 1
+
+# every symbol include/ntt256.h declares
+EXPORTS = [
+    "ntt256_ctx_create", "ntt256_ctx_create_named", "ntt256_ctx_destroy", "ntt256_ctx_set_tuning",
+    "ntt256_forward", "ntt256_inverse", "ntt256_forward_batch", "ntt256_inverse_batch",
+    "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2",
+    "ntt256_plan_describe", "ntt256_launch_count", "ntt256_strerror", "ntt256_last_cuda_error",
+    "ntt256_version",
+]
+
+
+class Ntt256Error(RuntimeError):
+    def __init__(self, status: int, detail: str = ""):
+        self.status = status
+        msg = lib().ntt256_strerror(status).decode()
+        super().__init__(f"ntt256 status {status}: {msg}{(' -- ' + detail) if detail else ''}")
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)"
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, u32p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32)
+        L.ntt256_ctx_create.argtypes = [ctypes.POINTER(vp), ci, u32p, u32p, ci]
+        L.ntt256_ctx_create_named.argtypes = [ctypes.POINTER(vp), ci, ci, ci]
+        L.ntt256_ctx_destroy.argtypes = [vp]
+        L.ntt256_ctx_destroy.restype = None
+        L.ntt256_ctx_set_tuning.argtypes = [vp, ci, ci]
+        for name in ("ntt256_forward", "ntt256_inverse"):
+            getattr(L, name).argtypes = [vp, vp, ci, vp]
+        for name in ("ntt256_forward_batch", "ntt256_inverse_batch"):
+            getattr(L, name).argtypes = [vp, vp, ci, ci, vp]
+        for name in ("ntt256_forward_host", "ntt256_inverse_host"):
+            getattr(L, name).argtypes = [vp, vp, vp, ci, ci]
+        for name in ("ntt256_fourstep_step1", "ntt256_fourstep_step2"):
+            getattr(L, name).argtypes = [vp, vp, ci, ci, ci, ci, vp]
+        L.ntt256_plan_describe.argtypes = [ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]
+        L.ntt256_plan_describe.restype = ctypes.c_size_t
+        L.ntt256_launch_count.argtypes = [vp]
+        L.ntt256_launch_count.restype = ctypes.c_ulonglong
+        L.ntt256_strerror.argtypes = [ci]
+        L.ntt256_strerror.restype = ctypes.c_char_p
+        L.ntt256_last_cuda_error.argtypes = [vp]
+        L.ntt256_last_cuda_error.restype = ctypes.c_char_p
+        L.ntt256_version.restype = ctypes.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def plan_describe(log_n: int, max_log_n: int, tile_bits: int = 10, coalesce_bits: int = 2) -> dict:
+    """Host-only: the pass plan ntt256_forward would run (JSON -> dict)."""
+    import json
+
+    L = lib()
+    need = L.ntt256_plan_describe(log_n, max_log_n, tile_bits, coalesce_bits, None, 0)
+    buf = ctypes.create_string_buffer(need)
+    L.ntt256_plan_describe(log_n, max_log_n, tile_bits, coalesce_bits, buf, need)
+    return json.loads(buf.value.decode())
