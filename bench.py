@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the 256-bit NTT hot path (BASELINE.json metric:
+256-bit NTT elements/s at 2^24 on 1/2/4/8 B200, with roofline fractions).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port of the
+                                                             # reference's CPU NTT on host cores
+    torchrun ... bench.py --gpus N ...                       # four-step over N GPUs (strong scaling)
+
+A "step" is one forward NTT of 2^24 BN254-Fr elements, in place, natural order in and out.
+`value` is elements/s with the input resident in HBM; `e2e` is the same metric through the
+host-buffer entry point of the C ABI (ntt256_forward_host: H2D + transform + D2H inside the
+timed region).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N = 24
+FIELD = "bn254_fr"
+METRIC = "ntt256_elements_per_s_2^24"
+UNIT = "elements/s"
+MACS_PER_MODMUL = 136  # 2*8^2 + 8 32x32->64 multiply-accumulates (SURVEY.md par. 8d)
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self._nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {
+            "sm_mhz": (s[len(s) // 2] if s else None),
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(s),
+        }
+
+
+def cpu_baseline(sample_log_n: int, threads: int, reps: int = 1):
+    """Times the oracle port of the reference's CPU NTT (big-num.cu:37-55 restated over the
+    256-bit field) on the host cores.  Returns (elements/s, seconds, description)."""
+    import numpy as np  # noqa: F401
+
+    from oracle import c_oracle
+    from ntt_b200.api import FIELDS
+
+    p, g = FIELDS[FIELD]
+    x = c_oracle.splitmix_elements(1 << sample_log_n, p, 0x4E5454 + 3)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        c_oracle.ntt(x, p, g, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return (1 << sample_log_n) / best, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The reference has no 256-bit CPU NTT (its
+    NTT() is int64 over a 29-bit prime), so this arm times the oracle port -- the same algorithm
+    over BN254 Fr -- with every host thread, on a bounded sample (2^20 points per step), and also
+    reports the literal reference NTT() (oracle/_ref, int64) for continuity."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+
+    threads = max(1, os.cpu_count() or 1)
+    sample_log_n = 20
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(sample_log_n, threads)
+    t_total = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_baseline(sample_log_n, threads)
+        t_total += dt
+    ms = t_total / args.steps * 1e3
+    value = (1 << sample_log_n) / (ms / 1e3)
+    extra = {}
+    ref = c_oracle.ref_lib()
+    if ref is not None:
+        import ctypes
+
+        import numpy as np
+
+        a = np.arange(1 << 20, dtype=np.int64)
+        t0 = time.perf_counter()
+        ref.ref_ntt_i64(a.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), 20)
+        extra["reference_i64_ntt"] = {
+            "value": (1 << 20) / (time.perf_counter() - t0), "unit": UNIT, "cores": 1,
+            "what": "reference NTT() compiled from /root/reference (int64, p=469762049), 2^20 points",
+        }
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (256-bit modular integer)", "data": "synthetic",
+        "config": {"workload": f"forward NTT, {FIELD}, bounded sample 2^{sample_log_n} points per step "
+                               f"of the 2^{LOG_N} workload", "field": FIELD},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"2^{sample_log_n}-point forward NTT per step, OpenMP over butterflies"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle  # checker for the correctness spot-check and the cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the NTT has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    p, g = FIELDS[FIELD]
+    n = 1 << LOG_N
+    ctx = Ntt256(FIELD, max_log_n=LOG_N, device=local_rank)
+    if args.tile_bits:
+        ctx.set_tuning(args.tile_bits, args.coalesce_bits)
+    stream = torch.cuda.current_stream()
+
+    if world == 1:
+        x_host = c_oracle.splitmix_elements(n, p, 0x4E5454 + 3)
+        d = torch.from_numpy(x_host.view(np.int32)).cuda()
+
+        def step():
+            ctx.forward(d, LOG_N)
+
+        fs = None
+    else:
+        from ntt_b200.dist import FourStep
+
+        fs = FourStep(ctx, LOG_N, world, rank)
+        x_shard = c_oracle.splitmix_elements(n // world, p, 0x4E5454 + 100 + rank)
+        fs.load_shard(torch.from_numpy(x_shard.view(np.int32)).cuda())
+
+        def step():
+            fs.forward()
+
+    # ---- correctness spot check before timing (one output via Horner on the CPU oracle)
+    if world == 1:
+        step()
+        torch.cuda.synchronize()
+        got = d[: 8 * 4].cpu().numpy().view(np.uint32).reshape(-1, 8)
+        for k in (1, 3):
+            want = c_oracle.dft_sample(x_host, p, g, k)
+            have = sum(int(got[k][i]) << (32 * i) for i in range(8))
+            if want != have:
+                raise AssertionError(f"bench: X[{k}] differs from the oracle")
+        d.copy_(torch.from_numpy(x_host.view(np.int32)))
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    launches = ctx.launch_count - launches0
+    ms_step = ms_total / args.steps
+    value = n / (ms_step / 1e3)
+
+    # ---- end to end through the host-buffer entry point (H2D + NTT + D2H in the timed region)
+    e2e = None
+    if world == 1:
+        h_in = torch.from_numpy(x_host.view(np.int32)).pin_memory()
+        h_out = torch.empty_like(h_in).pin_memory()
+        hin_np, hout_np = h_in.numpy().view(np.uint32), h_out.numpy().view(np.uint32)
+        for _ in range(2):
+            ctx.forward_host(hin_np, LOG_N, out=hout_np)
+        e2e_steps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.forward_host(hin_np, LOG_N, out=hout_np)
+        dt = (time.perf_counter() - t0) / e2e_steps
+        e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32,
+               "ms_per_step": dt * 1e3, "api": "ntt256_forward_host (pinned host buffers)"}
+    else:
+        e2e = fs.e2e(args) if hasattr(fs, "e2e") else None
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (ntt_pass_kernel): all launches of a step are that kernel
+    hbm_peak, peak_src = _peaks()
+    passes = launches / args.steps / (1 if world == 1 else 1)
+    launch_ms = ms_total / max(launches, 1)
+    n_local = n // world
+    alg_bytes_transform = 64.0 * n_local * -(-LOG_N // 12)  # 64 B/element per <=12-stage pass
+    alg_bytes_launch = alg_bytes_transform / max(passes, 1)
+    achieved = alg_bytes_launch / (launch_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    modmuls = (n / 2) * LOG_N
+    int_peak_macs = 18.3e12  # measured plain IMAD.WIDE rate, profiles/r01_microbench_pipes.jsonl
+    int_achieved = modmuls * MACS_PER_MODMUL / (ms_step / 1e3) / world
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32x8 (256-bit modular integer)", "data": "synthetic",
+        "config": {"workload": f"2^{LOG_N}-point forward NTT, {FIELD} (8x u32 limbs), in place, natural order in/out"
+                               + ("" if world == 1 else f", four-step over {world} GPUs with NCCL all-to-all"),
+                   "field": FIELD, "log_n": LOG_N, "passes_per_step": passes,
+                   "l2_policy": "input 512 MiB > 126 MB L2, no flush needed",
+                   "binding_roofline": "int32-multiply pipe (see roofline_int); HBM is ~6x off"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "kernel": "ntt_pass_kernel", "launch_ms": launch_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes_launch, "peak_source": peak_src},
+        "roofline_int": {"bound": "int32-mul", "achieved": int_achieved / 1e12, "peak": int_peak_macs / 1e12,
+                         "unit": "T wide-MAC/s", "frac": int_achieved / int_peak_macs,
+                         "work": "136 MACs x (n/2) log2 n modmuls (SURVEY 8d)",
+                         "peak_source": "measured IMAD.WIDE.U32 rate, profiles/r01_microbench_pipes.jsonl"},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = max(1, os.cpu_count() or 1)
+        v, secs = cpu_baseline(20, threads)
+        v1, secs1 = cpu_baseline(18, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"2^20-point forward NTT of the same field, {secs:.2f} s; "
+                                          f"single thread (reference convention) 2^18 points: {v1:.0f} elements/s"}
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tile-bits", type=int, default=0)
+    ap.add_argument("--coalesce-bits", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,84 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/ntt256.h declares,
+validates arguments before touching CUDA, and fails loudly (no CPU fallback) when no device
+can run it."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ntt_b200 import lib as L_mod  # noqa: F401  (package re-exports the loader)
+from ntt_b200.lib import EXPORTS, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header(built):
+    with open(os.path.join(ROOT, "include", "ntt256.h")) as f:
+        header = f.read()
+    declared = sorted(set(re.findall(r"\b(ntt256_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(EXPORTS)
+    L = lib()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_strings(built):
+    L = lib()
+    assert L.ntt256_strerror(0) == b"ok"
+    assert b"argument" in L.ntt256_strerror(1)
+    assert b"sm_100a" in L.ntt256_version()
+
+
+def _limbs(v):
+    return np.array([(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
+
+
+def _create(p, g, max_log_n):
+    L = lib()
+    h = ctypes.c_void_p()
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    rc = L.ntt256_ctx_create(ctypes.byref(h), 0, _limbs(p).ctypes.data_as(u32p), _limbs(g).ctypes.data_as(u32p), max_log_n)
+    return rc, h
+
+
+def test_argument_and_field_validation(built):
+    from ntt_b200.lib import ERR_ARG, ERR_FIELD
+
+    bn = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    assert _create(bn, 5, 0)[0] == ERR_ARG
+    assert _create(bn, 5, 33)[0] == ERR_ARG
+    assert _create(bn - 1, 5, 10)[0] == ERR_FIELD            # even modulus
+    assert _create((1 << 255) + 1, 5, 10)[0] == ERR_FIELD     # p >= 2^255: no lazy-reduction headroom
+    assert _create(bn, 5, 29)[0] == ERR_FIELD                 # two-adicity of BN254 Fr is 28
+    assert _create(bn, 0, 10)[0] == ERR_FIELD
+    assert _create(bn, 4, 10)[0] == ERR_FIELD                 # 4 is a square: w_N^(N/2) != -1
+    L = lib()
+    assert L.ntt256_forward(None, None, 3, None) == ERR_ARG
+    assert L.ntt256_ctx_create_named(ctypes.byref(ctypes.c_void_p()), 0, 7, 10) == ERR_ARG
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device context creation must fail with ERR_CUDA, never compute on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from ntt_b200.api import Ntt256
+    from ntt_b200.lib import ERR_CUDA, Ntt256Error
+
+    with pytest.raises(Ntt256Error) as e:
+        Ntt256("bn254_fr", max_log_n=12)
+    assert e.value.status == ERR_CUDA
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under ntt_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "ntt_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert "oracle" not in src.replace("CPU oracle NTT()", ""), f"{fn} mentions the oracle"

@@ -1,0 +1,290 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes -> libntt256.so),
+against the CPU oracle on the same seeded inputs -- bit-exact -- plus golden vectors and, at
+BASELINE.json's full sizes, size-independent properties (round trip, sampled outputs by
+Horner, linearity).  Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback to test")
+    torch.cuda.set_device(0)
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ctxs(torch_cuda):
+    from ntt_b200.api import Ntt256
+
+    made = {}
+
+    def get(field, max_log_n):
+        key = (field, max_log_n)
+        if key not in made:
+            made[key] = Ntt256(field, max_log_n=max_log_n)
+        return made[key]
+
+    yield get
+    for c in made.values():
+        c.close()
+
+
+def _gpu_forward(torch, ctx, x, log_n, batch=1, inverse=False):
+    d = torch.from_numpy(np.array(x, dtype=np.uint32, copy=True).view(np.int32)).cuda()
+    (ctx.inverse if inverse else ctx.forward)(d, log_n, batch)
+    torch.cuda.synchronize()
+    return d.cpu().numpy().view(np.uint32).reshape(-1, 8)
+
+
+# --------------------------------------------------------------------------- config 1
+@pytest.mark.parametrize("field", ["bn254_fr", "bls12_381_fr"])
+def test_all_sizes_vs_oracle(torch_cuda, ctxs, field):
+    """2^0 .. 2^16 points (config 1 of BASELINE.json is the 2^16 BN254 case), forward and inverse."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    p, g = FIELDS[field]
+    ctx = ctxs(field, 20)
+    for log_n in range(0, 17):
+        x = co.splitmix_elements(1 << log_n, p, 0x4E5454 + log_n)
+        want = co.ntt(x, p, g, threads=4)
+        got = _gpu_forward(torch_cuda, ctx, x, log_n)
+        assert np.array_equal(got, want), f"forward 2^{log_n}"
+        back = _gpu_forward(torch_cuda, ctx, got, log_n, inverse=True)
+        assert np.array_equal(back, x), f"inverse 2^{log_n}"
+        wanti = co.ntt(x, p, g, inverse=True, threads=4)
+        assert np.array_equal(_gpu_forward(torch_cuda, ctx, x, log_n, inverse=True), wanti)
+
+
+@pytest.mark.parametrize("tile_bits,coalesce_bits", [(6, 1), (8, 3), (10, 2), (11, 2), (12, 2), (12, 0)])
+def test_every_tiling_gives_the_same_bits(torch_cuda, tile_bits, coalesce_bits):
+    """Plan selection must not change results: sweep tile sizes / coalescing widths."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    p, g = FIELDS["bls12_381_fr"]
+    ctx = Ntt256("bls12_381_fr", max_log_n=18)
+    ctx.set_tuning(tile_bits, coalesce_bits)
+    for log_n in (7, 12, 13, 15, 18):
+        x = co.splitmix_elements(1 << log_n, p, 31 + log_n)
+        assert np.array_equal(_gpu_forward(torch_cuda, ctx, x, log_n), co.ntt(x, p, g, threads=4))
+    ctx.close()
+
+
+# --------------------------------------------------------------------------- reference KATs
+def test_reference_field_kats(torch_cuda):
+    """Created with the reference's own field (p = 469762049, g = 3, big-num.cu:9-10) and its own
+    input x[j] = j (big-num.cu:399-402), the library must reproduce the outputs of the
+    reference's NTT(): tests/golden/ref_i64_kat.json was generated from the reference's code."""
+    from ntt_b200.api import Ntt256
+
+    with open(os.path.join(GOLD, "ref_i64_kat.json")) as f:
+        gold = json.load(f)
+    ctx = Ntt256(p=gold["p"], g=gold["g"], max_log_n=20)
+    for case in gold["cases"]:
+        log_n = case["log_n"]
+        n = 1 << log_n
+        x = np.zeros((n, 8), dtype=np.uint32)
+        x[:, 0] = np.arange(n, dtype=np.uint32)  # int64_to_cgbn(i), big-num.cu:355-362
+        got = _gpu_forward(torch_cuda, ctx, x, log_n)
+        assert not got[:, 2:].any()
+        lo64 = got[:, 0].astype(np.int64) | (got[:, 1].astype(np.int64) << 32)  # cgbn_to_int64, :364-367
+        assert lo64[:8].tolist() == case["head"][: min(8, n)]
+        assert hashlib.sha256(lo64.tobytes()).hexdigest() == case["sha256_i64le"]
+    ctx.close()
+
+
+def test_bigfield_golden(torch_cuda, ctxs):
+    from oracle import py_oracle as po
+
+    with open(os.path.join(GOLD, "bigfield_kat.json")) as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        F = po.FIELDS[case["field"]]
+        n = 1 << case["log_n"]
+        vals = list(range(n)) if case["input"] == "iota" else po.splitmix_elements(n, F, case["seed"])
+        x = np.frombuffer(po.to_bytes(vals), dtype=np.uint32).reshape(n, 8)
+        got = _gpu_forward(torch_cuda, ctxs(case["field"], 20), x, case["log_n"])
+        assert hashlib.sha256(got.tobytes()).hexdigest() == case["sha256_image"]
+
+
+def test_reference_named_entry_points(torch_cuda):
+    """NTT_GZKP / NTT_GPU_Naive keep the reference's argument meaning (device data in place,
+    host prime, omega = generator) and both equal the CPU NTT (big-num.cu:439-467)."""
+    from ntt_b200.api import FIELDS, NTT_GPU_Naive, NTT_GZKP
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    for kk in (5, 9, 14):  # the reference sweeps kk = 5..24 (big-num.cu:370)
+        length = 1 << kk
+        x = co.splitmix_elements(length, p, kk)
+        want = co.ntt(x, p, g, threads=4)
+        d1 = torch.from_numpy(x.view(np.int32)).cuda()
+        NTT_GPU_Naive(d1, length, None, 0, prime=p, omega=g)
+        d2 = torch.from_numpy(x.view(np.int32)).cuda()
+        NTT_GZKP(d2, length, None, 0, prime=co.limbs(p), omega=co.limbs(g), B=5, G=8)
+        torch.cuda.synchronize()
+        assert np.array_equal(d1.cpu().numpy().view(np.uint32), want)
+        assert np.array_equal(d2.cpu().numpy().view(np.uint32), want)
+    with pytest.raises(ValueError):
+        NTT_GZKP(d1, 48, prime=p, omega=g)
+
+
+# --------------------------------------------------------------------------- config 2
+def test_config2_bls_2p20_forward_inverse(torch_cuda, ctxs):
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    p, g = FIELDS["bls12_381_fr"]
+    ctx = ctxs("bls12_381_fr", 20)
+    x = co.splitmix_elements(1 << 20, p, 0x4E5454 + 2)
+    fwd = _gpu_forward(torch_cuda, ctx, x, 20)
+    assert np.array_equal(fwd, co.ntt(x, p, g, threads=8))
+    assert np.array_equal(_gpu_forward(torch_cuda, ctx, fwd, 20, inverse=True), x)
+
+
+# --------------------------------------------------------------------------- config 3 (one GPU's share)
+def test_batches(torch_cuda, ctxs):
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 20)
+    for log_n, batch in ((1, 5), (2, 7), (4, 3), (10, 9), (12, 32), (16, 4)):
+        n = 1 << log_n
+        x = co.splitmix_elements(n * batch, p, 500 + log_n)
+        got = _gpu_forward(torch_cuda, ctx, x, log_n, batch=batch)
+        for b in range(batch):
+            assert np.array_equal(got[b * n:(b + 1) * n], co.ntt(x[b * n:(b + 1) * n], p, g)), (log_n, b)
+        back = _gpu_forward(torch_cuda, ctx, got, log_n, batch=batch, inverse=True)
+        assert np.array_equal(back, x)
+
+
+def test_config3_batch256_of_2p16_properties(torch_cuda, ctxs):
+    """256 x 2^16 (512 MiB): every transform must equal the single-transform result of the same
+    data (checked bit-exactly on 3 of them) and the batch must round-trip."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 20)
+    n, batch = 1 << 16, 256
+    x = co.splitmix_elements(n * batch, p, 0x4E5454 + 3)
+    d = torch.from_numpy(x.view(np.int32)).cuda().view(-1)
+    ctx.forward(d, 16, batch)
+    torch.cuda.synchronize()
+    for b in (0, 101, 255):
+        got = d[b * n * 8:(b + 1) * n * 8].cpu().numpy().view(np.uint32).reshape(n, 8)
+        assert np.array_equal(got, co.ntt(x[b * n:(b + 1) * n], p, g, threads=8))
+    ctx.inverse(d, 16, batch)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 8), x)
+
+
+# --------------------------------------------------------------------------- configs 4/5 on one GPU
+@pytest.mark.parametrize("field,log_n", [("bn254_fr", 24), ("bls12_381_fr", 22)])
+def test_large_transform_properties(torch_cuda, ctxs, field, log_n):
+    """Full-size checks that need no full second oracle run: sampled outputs by Horner on the
+    CPU, linearity NTT(x+y) = NTT(x)+NTT(y), and inverse(forward(x)) == x."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS[field]
+    ctx = ctxs(field, 24)
+    n = 1 << log_n
+    x = co.splitmix_elements(n, p, 0x4E5454 + 4)
+    y = co.splitmix_elements(n, p, 0x4E5454 + 5)
+    X = _gpu_forward(torch, ctx, x, log_n)
+    for k in (0, 1, n // 2 + 7, n - 1):
+        assert co.dft_sample(x, p, g, k) == co.array_to_ints(X[k:k + 1])[0], k
+    Y = _gpu_forward(torch, ctx, y, log_n)
+    S = _gpu_forward(torch, ctx, co.vec_add(x, y, p), log_n)
+    assert np.array_equal(S, co.vec_add(X, Y, p))
+    assert np.array_equal(_gpu_forward(torch, ctx, X, log_n, inverse=True), x)
+    assert (co.array_to_ints(X[:64]) < np.array([p] * 64, dtype=object)).all()  # canonical outputs
+
+
+def test_full_oracle_2p22(torch_cuda, ctxs):
+    """Largest size the multi-threaded oracle finishes in seconds: full bit-exact comparison."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    p, g = FIELDS["bn254_fr"]
+    x = co.splitmix_elements(1 << 22, p, 99)
+    assert np.array_equal(_gpu_forward(torch_cuda, ctxs("bn254_fr", 24), x, 22), co.ntt(x, p, g, threads=16))
+
+
+# --------------------------------------------------------------------------- edge cases
+def test_edge_values(torch_cuda, ctxs):
+    """0, 1, p-1 and constant inputs: maximal carries through the lazy-reduction paths."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    for field in ("bn254_fr", "bls12_381_fr"):
+        p, g = FIELDS[field]
+        ctx = ctxs(field, 20)
+        for log_n in (3, 10, 13):
+            n = 1 << log_n
+            for vals in ([p - 1] * n, [0] * n, [1] + [0] * (n - 1), [(p - 1) if i % 2 else 0 for i in range(n)],
+                         [p - 1 - i for i in range(n)]):
+                x = co.ints_to_array(vals)
+                assert np.array_equal(_gpu_forward(torch_cuda, ctx, x, log_n), co.ntt(x, p, g, threads=4))
+
+
+def test_host_entry_point_and_errors(torch_cuda, ctxs):
+    from ntt_b200.api import FIELDS
+    from ntt_b200.lib import ERR_ARG, Ntt256Error
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 20)
+    x = co.splitmix_elements(3 << 12, p, 12)
+    got = ctx.forward_host(x, 12, batch=3)
+    for b in range(3):
+        assert np.array_equal(got[b << 12:(b + 1) << 12], co.ntt(x[b << 12:(b + 1) << 12], p, g))
+    assert np.array_equal(ctx.inverse_host(got, 12, batch=3), x)
+    d = torch.zeros(8 << 21, dtype=torch.int32, device="cuda")
+    with pytest.raises(Ntt256Error) as e:
+        ctx.forward(d, 21)  # beyond max_log_n of this context
+    assert e.value.status == ERR_ARG
+    with pytest.raises(ValueError):
+        ctx.forward(d, 20)  # buffer size does not match
+    with pytest.raises(TypeError):
+        ctx.forward(x, 12)  # host array passed to a device entry point
+    before = ctx.launch_count
+    ctx.forward(torch.zeros(8 << 10, dtype=torch.int32, device="cuda"), 10)
+    assert ctx.launch_count > before
+
+
+def test_streams_are_respected(torch_cuda, ctxs):
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 20)
+    x = co.splitmix_elements(1 << 14, p, 3)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        d = torch.from_numpy(x.view(np.int32)).cuda(non_blocking=False)
+        ctx.forward(d, 14)
+        ctx.inverse(d, 14)
+        ctx.forward(d, 14)
+    s.synchronize()
+    assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 8), co.ntt(x, p, g, threads=4))

@@ -1,0 +1,138 @@
+"""The oracle against every vector that pins it: the reference's own compiled CPU code
+(oracle/_ref, when present), golden vectors generated from it, the survey-time anchors, the
+DFT definition and the second (self-sort-in-place) statement of the algorithm."""
+import ctypes
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import py_oracle as po
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    with open(os.path.join(GOLD, name)) as f:
+        return json.load(f)
+
+
+def test_ref29_survey_kats(built):
+    a = _load("anchors.json")["ref29"]
+    F = po.REF29
+    assert po.ntt_ref(list(range(8)), F) == a["8"]
+    assert po.ntt_ref(list(range(16)), F)[:8] == a["16_head"]
+    assert po.ntt_ref(list(range(1024)), F)[:8] == a["1024_head"]
+    assert F.omega(256) == a["omega_256"]  # also hard-coded in /root/reference/src/twiddlecheck.py:11
+
+
+@pytest.mark.parametrize("impl", ["py", "c", "c_mt", "c_ssip", "py_ssip"])
+def test_reference_golden_vectors(built, impl):
+    """Outputs of the reference's own NTT() (p = 469762049, x[j] = j), tests/golden/ref_i64_kat.json."""
+    g = _load("ref_i64_kat.json")
+    F = po.Field("ref", g["p"], g["g"])
+    for case in g["cases"]:
+        log_n = case["log_n"]
+        n = 1 << log_n
+        if impl.startswith("py") and log_n > 12:
+            continue
+        x = list(range(n))
+        if impl == "py":
+            X = po.ntt_ref(x, F)
+        elif impl == "py_ssip":
+            X = po.ntt_ssip(x, F)
+        elif impl == "c":
+            X = co.array_to_ints(co.ntt(co.ints_to_array(x), F.p, F.g))
+        elif impl == "c_mt":
+            X = co.array_to_ints(co.ntt(co.ints_to_array(x), F.p, F.g, threads=4))
+        else:
+            X = co.array_to_ints(co.ntt_ssip(co.ints_to_array(x), F.p, F.g))
+        assert X[:8] == case["head"][: min(8, n)]
+        assert X[-4:] == case["tail"][-min(4, n):]
+        assert hashlib.sha256(np.array(X, dtype=np.int64).tobytes()).hexdigest() == case["sha256_i64le"]
+        if "full" in case:
+            assert X == case["full"]
+
+
+def test_against_compiled_reference(built):
+    """Live comparison with the reference's compiled CPU functions (only where oracle/_ref exists)."""
+    R = co.ref_lib()
+    if R is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    i64p = ctypes.POINTER(ctypes.c_longlong)
+    rng = np.random.default_rng(5)
+    P = int(R.ref_modulus())
+    for log_n in (1, 2, 3, 7, 10, 13):
+        n = 1 << log_n
+        # NOTE the reference's harness input is x[j] = j; random inputs are run through the same code
+        x = rng.integers(0, P, size=n, dtype=np.int64)
+        a = x.copy()
+        R.ref_ntt_i64(a.ctypes.data_as(i64p), log_n)
+        b = x.copy()
+        R.ref_ssip_i64(b.ctypes.data_as(i64p), log_n)
+        c = co.array_to_ints(co.ntt(co.ints_to_array(x.tolist()), P, int(R.ref_generator())))
+        assert a.tolist() == c
+        assert b.tolist() == c
+
+
+def test_bigfield_golden(built):
+    g = _load("bigfield_kat.json")
+    for case in g["cases"]:
+        F = po.FIELDS[case["field"]]
+        n = 1 << case["log_n"]
+        x = list(range(n)) if case["input"] == "iota" else po.splitmix_elements(n, F, case["seed"])
+        X = co.ntt(co.ints_to_array(x), F.p, F.g)
+        assert hashlib.sha256(X.tobytes()).hexdigest() == case["sha256_image"]
+        assert [hex(v) for v in co.array_to_ints(X[:4])] == case["head"]
+        if case["log_n"] <= 10:
+            assert po.sha256_image(po.ntt_ref(x, F)) == case["sha256_image"]
+
+
+def test_survey_anchors(built):
+    a = _load("anchors.json")
+    for name in ("bn254_fr", "bls12_381_fr"):
+        F = po.FIELDS[name]
+        X8 = po.ntt_ref(list(range(8)), F)
+        assert X8[0] == 0x1C and X8[4] == F.p - 4
+        assert X8[1] == int(a[name]["n8_X1"], 16)
+        X10 = co.ntt(co.ints_to_array(range(1 << 10)), F.p, F.g)
+        assert hashlib.sha256(X10.tobytes()).hexdigest() == a[name]["sha256_2^10"]
+        X16 = co.ntt(co.ints_to_array(range(1 << 16)), F.p, F.g, threads=4)
+        assert hashlib.sha256(X16.tobytes()).hexdigest() == a[name]["sha256_2^16"]
+        assert co.array_to_ints(X16[1:2])[0] == int(a[name]["2^16_X1"], 16)
+
+
+@pytest.mark.parametrize("name", ["ref29", "bn254_fr", "bls12_381_fr"])
+def test_definition_and_statements_agree(built, name):
+    F = po.FIELDS[name]
+    for log_n in range(0, 7):
+        x = po.splitmix_elements(1 << log_n, F, 77 + log_n)
+        want = po.dft_direct(x, F)
+        assert po.ntt_ref(x, F) == want
+        if log_n:
+            assert po.ntt_ssip(x, F) == want
+        arr = co.ints_to_array(x)
+        assert co.array_to_ints(co.ntt(arr, F.p, F.g)) == want
+        if log_n:
+            assert co.array_to_ints(co.ntt_ssip(arr, F.p, F.g)) == want
+        assert co.array_to_ints(co.ntt(co.ntt(arr, F.p, F.g), F.p, F.g, inverse=True)) == x
+        assert po.ntt_ref(want, F, inverse=True) == x
+
+
+def test_c_oracle_helpers(built):
+    F = po.BLS12_381_FR
+    x = co.splitmix_elements(1 << 11, F.p, 9)
+    assert co.array_to_ints(x) == po.splitmix_elements(1 << 11, F, 9)
+    assert all(v < F.p for v in co.array_to_ints(x))
+    X = co.ntt(x, F.p, F.g, threads=3)
+    assert np.array_equal(X, co.ntt(x, F.p, F.g, threads=1))
+    for k in (0, 1, 1000, 2047):
+        assert co.dft_sample(x, F.p, F.g, k) == co.array_to_ints(X[k : k + 1])[0]
+    y = co.splitmix_elements(1 << 11, F.p, 10)
+    s = co.vec_add(x, y, F.p)
+    assert co.array_to_ints(s) == [(a + b) % F.p for a, b in zip(co.array_to_ints(x), co.array_to_ints(y))]
+    with pytest.raises(ValueError):
+        co.ntt(co.ints_to_array(range(8)), 469762049 * 2 + 1, 3)  # 2^3 does not divide p-1 = 2*469762049

@@ -1,0 +1,56 @@
+"""Host logic without a GPU: the C++ planner (through ntt256_plan_describe) and the descriptor
+semantics, executed by the Python model of the kernel (plan_sim.py) against the oracle."""
+import random
+
+import pytest
+
+import plan_sim
+from ntt_b200.lib import plan_describe
+from oracle import py_oracle as po
+
+
+def _check_plan_invariants(plan, L, T, g):
+    assert plan["log_n"] == L
+    total = 0
+    for pd in plan["passes"]:
+        assert 3 <= pd["T"] <= T
+        assert pd["T"] + pd["nblk_bits"] == L
+        assert sorted(pd["in_pos"] + pd["blk_pos"]) == list(range(L))
+        assert sorted(pd["in_pos"]) == sorted(pd["out_pos"])  # in place: a tile stores where it loaded
+        if L > T:
+            for b in range(min(g, L)):
+                assert b in pd["in_pos"], "coalescing bits must be inside every tile"
+        total += pd["d"]
+        assert sum(pd["round_nb"]) == pd["d"]
+        for r in range(pd["nrounds"]):
+            sb = pd["round_sb"][r]
+            tm = pd["tmap"][r]
+            assert sorted(tm + [sb, sb + 1, sb + 2]) == list(range(pd["T"]))
+    assert total == L
+    assert plan["passes"][-1]["is_final"] == 1 and plan["passes"][-1]["has_tw"] == 0
+
+
+@pytest.mark.parametrize("L,T,g", [(3, 3, 0), (5, 5, 0), (8, 8, 2), (6, 4, 1), (8, 4, 1), (9, 5, 1), (10, 6, 2),
+                                   (11, 6, 1), (12, 6, 2), (12, 7, 2), (13, 8, 3), (12, 12, 2), (13, 10, 2)])
+def test_plan_executes_to_the_oracle(built, L, T, g):
+    plan = plan_describe(L, 14, T, g)
+    assert "error" not in plan
+    _check_plan_invariants(plan, L, T, g)
+    rng = random.Random(L * 100 + T)
+    for F in (po.BN254_FR, po.REF29):
+        x = [rng.randrange(F.p) for _ in range(1 << L)]
+        want = po.ntt_ref(x, F)
+        assert plan_sim.run_plan(x, plan, F.p, F.g, 14) == want
+        assert plan_sim.run_plan(want, plan, F.p, F.g, 14, inverse=True) == x
+
+
+@pytest.mark.parametrize("L", [16, 20, 24, 26, 28])
+def test_production_plans_exist_and_are_short(built, L):
+    for T, g, max_passes in ((10, 2, 5), (11, 2, 5), (12, 2, 4)):
+        plan = plan_describe(L, 28, T, g)
+        assert "error" not in plan, (L, T, g)
+        _check_plan_invariants(plan, L, T, g)
+        assert len(plan["passes"]) <= max_passes
+    # the headline configuration: 2^24 in three in-place passes with 128-byte runs
+    if L == 24:
+        assert len(plan_describe(24, 24, 12, 2)["passes"]) == 3
