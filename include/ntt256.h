@@ -86,8 +86,11 @@ int ntt256_inverse_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_
  *   Input shard of rank r: x[j1*C + j2] for j2 in [r*C/P, (r+1)*C/P), packed row-major R x (C/P).
  *   step1: R-point column NTTs + twiddle w_n^(j2*k1), in place.
  *   exchange: rank r sends rows k1 in [s*R/P, (s+1)*R/P) to rank s (contiguous chunks).
- *   step2: on the received buffer laid out [src rank][k1 local][j2 local], C-point row NTTs;
- *          output shard of rank r: X[k1 + R*k2] for k1 in block r, packed (R/P) x C. */
+ *   step2: on the received buffer laid out [src rank][k1 local][j2 local], C-point row NTTs.
+ *          Output shard of rank r: X[k1 + R*k2] for k1 in block r, stored as P blocks of
+ *          (R/P) x (C/P): element index = ((k2 mod P)*(R/P) + k1_local)*(C/P) + (k2 div P)
+ *          (each index field is transformed where it lies, which keeps step 2 to one pass for
+ *          C <= 4096; ntt_b200.dist.gather_output() turns the shards into natural order). */
 int ntt256_fourstep_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
                           ntt256_stream stream);
 int ntt256_fourstep_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
@@ -97,6 +100,9 @@ int ntt256_fourstep_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, 
  * ntt256_forward would run for 2^log_n points.  Returns the number of bytes needed
  * (including the NUL); writes at most buf_len bytes. */
 size_t ntt256_plan_describe(int log_n, int max_log_n, int tile_bits, int coalesce_bits, char* buf, size_t buf_len);
+/* Same for one local step (1 or 2) of the four-step decomposition on `rank`. */
+size_t ntt256_plan_describe_fourstep(int step, int log_n, int log_r, int log_p, int rank, int max_log_n, int tile_bits,
+                                     int coalesce_bits, char* buf, size_t buf_len);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 unsigned long long ntt256_launch_count(const ntt256_ctx* ctx);
 

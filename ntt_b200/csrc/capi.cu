@@ -106,43 +106,58 @@ int build_power_table(ntt256_ctx* ctx, uint4** out, const U256& base_mont, int b
   return NTT256_OK;
 }
 
+// Plan request of a whole transform (kind 0) or of one local step of the four-step
+// decomposition (kinds 1 and 2, SURVEY.md par. 8e), expressed in the planner's label model.
+PlanRequest build_request(const PlanKey& key, int tile_bits, int coalesce_bits, int max_log_n) {
+  PlanRequest req;
+  req.tile_bits = tile_bits;
+  req.coalesce_bits = coalesce_bits;
+  req.max_log_n = max_log_n;
+  req.log_n = key.log_n;
+  if (key.kind != 0) {
+    const int L = key.log_n, lr = key.log_r, lp = key.log_p, lc = L - lr;
+    const int nloc = L - lp;
+    req.total_log_n = L;
+    req.start.resize(nloc);
+    req.target.resize(nloc);
+    if (key.kind == 1) {
+      // local index = j1 * (C/P) + j2_local ; rank = top lp bits of j2
+      for (int p = 0; p < lc - lp; ++p) req.start[p] = p, req.target[p] = p;
+      for (int i = 0; i < lr; ++i) {
+        req.start[lc - lp + i] = lc + i;
+        req.target[lc - lp + i] = 64 + i;  // k1 natural above j2_local
+      }
+      req.time_hi = L - 1;
+      req.time_lo = lc;
+      req.jlow_const = (uint32_t)key.rank << (lc - lp);
+    } else {
+      // received layout [src rank][k1 local][j2 local]
+      for (int p = 0; p < lc - lp; ++p) req.start[p] = p;
+      for (int c = 0; c < lr - lp; ++c) req.start[lc - lp + c] = 64 + c;
+      for (int i = 0; i < lp; ++i) req.start[lc - lp + lr - lp + i] = lc - lp + i;
+      // output [k2 mod P][k1 local][k2 div P]: every field is transformed where it lies (the two
+      // j2 fields are bit-reversed in place), so a C-point row NTT with C <= 2^tile_bits is ONE pass.
+      // k2 bit i = k_{lr+i}; bits 0..lp-1 come from the old rank bits on top.
+      for (int i = 0; i < lc - lp; ++i) req.target[i] = 64 + lr + lp + i;
+      for (int c = 0; c < lr - lp; ++c) req.target[lc - lp + c] = 64 + c;
+      for (int i = 0; i < lp; ++i) req.target[lc - lp + lr - lp + i] = 64 + lr + i;
+      req.time_hi = lc - 1;
+      req.time_lo = 0;
+      req.jlow_const = 0;
+    }
+  }
+  return req;
+}
+
+bool fourstep_args_ok(int log_n, int log_r, int log_p, int rank) {
+  return log_p >= 0 && log_r >= log_p && log_n - log_r >= log_p && rank >= 0 && rank < (1 << log_p) &&
+         log_n - log_p >= 3 && log_r >= 1 && log_n - log_r >= 1;
+}
+
 int get_plan(ntt256_ctx* ctx, const PlanKey& key, const Plan** out) {
   auto it = ctx->plans.find(key);
   if (it == ctx->plans.end()) {
-    PlanRequest req;
-    req.tile_bits = ctx->tile_bits;
-    req.coalesce_bits = ctx->coalesce_bits;
-    req.max_log_n = ctx->max_log_n;
-    req.log_n = key.log_n;
-    if (key.kind != 0) {
-      const int L = key.log_n, lr = key.log_r, lp = key.log_p, lc = L - lr;
-      const int nloc = L - lp;
-      req.total_log_n = L;
-      req.start.resize(nloc);
-      req.target.resize(nloc);
-      if (key.kind == 1) {
-        // local index = j1 * (C/P) + j2_local ; rank = top lp bits of j2
-        for (int p = 0; p < lc - lp; ++p) req.start[p] = p, req.target[p] = p;
-        for (int i = 0; i < lr; ++i) {
-          req.start[lc - lp + i] = lc + i;
-          req.target[lc - lp + i] = 64 + i;  // k1 natural above j2_local
-        }
-        req.time_hi = L - 1;
-        req.time_lo = lc;
-        req.jlow_const = (uint32_t)key.rank << (lc - lp);
-      } else {
-        // received layout [src rank][k1 local][j2 local]
-        for (int p = 0; p < lc - lp; ++p) req.start[p] = p;
-        for (int c = 0; c < lr - lp; ++c) req.start[lc - lp + c] = 64 + c;
-        for (int i = 0; i < lp; ++i) req.start[lc - lp + lr - lp + i] = lc - lp + i;
-        // output [k1 local][k2]: k2 bit i = k_{lr+i}
-        for (int i = 0; i < lc; ++i) req.target[i] = 64 + lr + i;
-        for (int c = 0; c < lr - lp; ++c) req.target[lc + c] = 64 + c;
-        req.time_hi = lc - 1;
-        req.time_lo = 0;
-        req.jlow_const = 0;
-      }
-    }
+    PlanRequest req = build_request(key, ctx->tile_bits, ctx->coalesce_bits, ctx->max_log_n);
     Plan plan;
     if (!make_plan(req, &plan)) return NTT256_ERR_PLAN;
     it = ctx->plans.emplace(key, plan).first;
@@ -380,9 +395,7 @@ int ntt256_inverse_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_
 
 static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log_r, int log_p, int rank,
                     cudaStream_t stream) {
-  if (!ctx || !d_shard || log_n > ctx->max_log_n || log_p < 0 || log_r < log_p || log_n - log_r < log_p ||
-      rank < 0 || rank >= (1 << log_p) || log_n - log_p < 3)
-    return NTT256_ERR_ARG;
+  if (!ctx || !d_shard || log_n > ctx->max_log_n || !fourstep_args_ok(log_n, log_r, log_p, rank)) return NTT256_ERR_ARG;
   CTX_CUDA(cudaSetDevice(ctx->device));
   const Plan* plan = nullptr;
   // step 2 does not depend on the rank (no foreign time bits remain)
@@ -409,6 +422,23 @@ size_t ntt256_plan_describe(int log_n, int max_log_n, int tile_bits, int coalesc
   Plan plan;
   std::string s;
   if (log_n < 3 || !make_plan(req, &plan))
+    s = "{\"error\": \"no plan\"}";
+  else
+    s = plan.describe();
+  if (buf && buf_len) {
+    size_t n = std::min(buf_len - 1, s.size());
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return s.size() + 1;
+}
+
+size_t ntt256_plan_describe_fourstep(int step, int log_n, int log_r, int log_p, int rank, int max_log_n, int tile_bits,
+                                     int coalesce_bits, char* buf, size_t buf_len) {
+  std::string s;
+  Plan plan;
+  if ((step != 1 && step != 2) || !fourstep_args_ok(log_n, log_r, log_p, rank) || max_log_n < log_n ||
+      !make_plan(build_request(PlanKey{step, log_n, log_r, log_p, rank}, tile_bits, coalesce_bits, max_log_n), &plan))
     s = "{\"error\": \"no plan\"}";
   else
     s = plan.describe();

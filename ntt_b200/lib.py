@@ -18,7 +18,7 @@ EXPORTS = [
     "ntt256_ctx_create", "ntt256_ctx_create_named", "ntt256_ctx_destroy", "ntt256_ctx_set_tuning",
     "ntt256_forward", "ntt256_inverse", "ntt256_forward_batch", "ntt256_inverse_batch",
     "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2",
-    "ntt256_plan_describe", "ntt256_launch_count", "ntt256_strerror", "ntt256_last_cuda_error",
+    "ntt256_plan_describe", "ntt256_plan_describe_fourstep", "ntt256_launch_count", "ntt256_strerror", "ntt256_last_cuda_error",
     "ntt256_version",
 ]
 
@@ -55,6 +55,8 @@ def lib() -> ctypes.CDLL:
             getattr(L, name).argtypes = [vp, vp, ci, ci, ci, ci, vp]
         L.ntt256_plan_describe.argtypes = [ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]
         L.ntt256_plan_describe.restype = ctypes.c_size_t
+        L.ntt256_plan_describe_fourstep.argtypes = [ci] * 8 + [ctypes.c_char_p, ctypes.c_size_t]
+        L.ntt256_plan_describe_fourstep.restype = ctypes.c_size_t
         L.ntt256_launch_count.argtypes = [vp]
         L.ntt256_launch_count.restype = ctypes.c_ulonglong
         L.ntt256_strerror.argtypes = [ci]
@@ -74,4 +76,17 @@ def plan_describe(log_n: int, max_log_n: int, tile_bits: int = 10, coalesce_bits
     need = L.ntt256_plan_describe(log_n, max_log_n, tile_bits, coalesce_bits, None, 0)
     buf = ctypes.create_string_buffer(need)
     L.ntt256_plan_describe(log_n, max_log_n, tile_bits, coalesce_bits, buf, need)
+    return json.loads(buf.value.decode())
+
+
+def plan_describe_fourstep(step: int, log_n: int, log_r: int, log_p: int, rank: int, max_log_n: int,
+                           tile_bits: int = 10, coalesce_bits: int = 2) -> dict:
+    """Host-only: the plan of local step 1 or 2 of the four-step decomposition on `rank`."""
+    import json
+
+    L = lib()
+    a = (step, log_n, log_r, log_p, rank, max_log_n, tile_bits, coalesce_bits)
+    need = L.ntt256_plan_describe_fourstep(*a, None, 0)
+    buf = ctypes.create_string_buffer(need)
+    L.ntt256_plan_describe_fourstep(*a, buf, need)
     return json.loads(buf.value.decode())

@@ -288,3 +288,35 @@ def test_streams_are_respected(torch_cuda, ctxs):
         ctx.forward(d, 14)
     s.synchronize()
     assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 8), co.ntt(x, p, g, threads=4))
+
+
+# --------------------------------------------------------------------------- configs 4/5: four-step pieces
+@pytest.mark.parametrize("log_n,world", [(12, 1), (16, 2), (16, 8), (20, 4), (21, 8)])
+def test_fourstep_ranks_emulated_on_one_gpu(torch_cuda, ctxs, log_n, world):
+    """Every rank's step 1 and step 2 run on this GPU one after the other, the all-to-all is
+    replaced by its host definition (ntt_b200.dist.exchange_reference): scatter -> step1 ->
+    exchange -> step2 -> gather must equal the single-transform oracle bit for bit."""
+    from ntt_b200 import dist as nd
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 24)
+    log_p = world.bit_length() - 1
+    log_r = nd.default_log_r(log_n)
+    x = co.splitmix_elements(1 << log_n, p, 0x4E5454 + 40 + log_n)
+    want = co.ntt(x, p, g, threads=8)
+    s1 = []
+    for r, sh in enumerate(nd.scatter_input(x, log_n, world, log_r)):
+        d = torch.from_numpy(sh.view(np.int32)).cuda().view(-1)
+        ctx.fourstep_step1(d, log_n, log_r, log_p, r)
+        torch.cuda.synchronize()
+        s1.append(d.cpu().numpy().view(np.uint32).reshape(-1, 8))
+    s2 = []
+    for r, sh in enumerate(nd.exchange_reference(s1, world)):
+        d = torch.from_numpy(np.ascontiguousarray(sh).view(np.int32)).cuda().view(-1)
+        ctx.fourstep_step2(d, log_n, log_r, log_p, r)
+        torch.cuda.synchronize()
+        s2.append(d.cpu().numpy().view(np.uint32).reshape(-1, 8))
+    assert np.array_equal(nd.gather_output(s2, log_n, world, log_r), want)
