@@ -1,0 +1,136 @@
+"""Limb-exact Python model of mont_mul() in ntt_b200/csrc/field.cuh (even/odd CIOS on 32-bit
+limbs).  Checks the value identity r = a*b*2^-256 mod p with r < 2p and, above all, the two
+claims the CUDA code relies on but cannot assert at run time: the odd accumulator chain never
+carries out of limb 7, and Y[7] never overflows when the even chain's carry is folded in."""
+import random
+
+import pytest
+
+from oracle import py_oracle as po
+
+M32 = 0xFFFFFFFF
+
+
+def _limbs(v):
+    return [(v >> (32 * i)) & M32 for i in range(8)]
+
+
+def _val(l):
+    return sum(x << (32 * i) for i, x in enumerate(l))
+
+
+class Overflow(Exception):
+    pass
+
+
+def _mad_row(acc, a4, b):
+    """acc[0..7] += (a4[0..3]) * b laid at limb pairs; returns carry out (as mad_row in field.cuh)."""
+    c = 0
+    for j in range(4):
+        prod = a4[j] * b
+        t = acc[2 * j] + (prod & M32) + c
+        acc[2 * j] = t & M32
+        c = t >> 32
+        t = acc[2 * j + 1] + (prod >> 32) + c
+        acc[2 * j + 1] = t & M32
+        c = t >> 32
+    return c
+
+
+def mont_mul_model(a, b, p, np0):
+    al, bl, pl = _limbs(a), _limbs(b), _limbs(p)
+    ae, ao = al[0::2], al[1::2]
+    pe, podd = pl[0::2], pl[1::2]
+    X = [0] * 8
+    Y = [0] * 8
+    for j in range(4):
+        pr = ae[j] * bl[0]
+        X[2 * j], X[2 * j + 1] = pr & M32, pr >> 32
+        pr = ao[j] * bl[0]
+        Y[2 * j], Y[2 * j + 1] = pr & M32, pr >> 32
+
+    def redc():
+        m = (X[0] * np0) & M32
+        cx = _mad_row(X, pe, m)
+        cy = _mad_row(Y, podd, m)
+        if cy:
+            raise Overflow("odd chain carried out")
+        if Y[7] + cx > M32:
+            raise Overflow("Y[7] overflow on carry fold")
+        Y[7] += cx
+        assert X[0] == 0
+
+    redc()
+    for i in range(1, 8):
+        # shift_mad_row
+        t = Y[0] + X[1]
+        nX0, c = t & M32, t >> 32
+        nY = [X[2], X[3], X[4], X[5], X[6], X[7], 0, 0]
+        # nY += a_odd * b_i with carry-in c
+        cc = c
+        for j in range(4):
+            pr = ao[j] * bl[i]
+            t = nY[2 * j] + (pr & M32) + cc
+            nY[2 * j], cc = t & M32, t >> 32
+            t = nY[2 * j + 1] + (pr >> 32) + cc
+            nY[2 * j + 1], cc = t & M32, t >> 32
+        if cc:
+            raise Overflow("nY chain carried out")
+        nX = [nX0] + Y[1:8]
+        cx = _mad_row(nX, ae, bl[i])
+        if nY[7] + cx > M32:
+            raise Overflow("nY[7] overflow")
+        nY[7] += cx
+        X[:] = nX
+        Y[:] = nY
+        redc()
+    r = _val(Y) + (_val(X) >> 32)
+    if r >> 256:
+        raise Overflow("result exceeds 256 bits")
+    return r
+
+
+FIELDS = [po.BN254_FR, po.BLS12_381_FR, po.REF29, po.Field("p255m19", (1 << 255) - 19, 2)]
+
+
+@pytest.mark.parametrize("F", FIELDS, ids=lambda f: f.name)
+def test_mont_mul_model_value_and_no_overflow(F):
+    p = F.p
+    np0 = (-pow(p, -1, 1 << 32)) % (1 << 32)
+    Rinv = pow(1 << 256, -1, p)
+    rng = random.Random(12345)
+    two_p = 2 * p
+    specials_a = [0, 1, p - 1, p - 2, (p - 1) // 2, p >> 1, 0xFFFFFFFF, p & ~M32]
+    specials_b = [0, 1, p - 1, p, two_p - 1, two_p - 2, (1 << 255) - 1 if two_p > (1 << 255) else two_p - 1,
+                  min(two_p - 1, (1 << 256) - 1), _val([M32] * 7 + [_limbs(two_p - 1)[7]]) % two_p]
+    cases = [(a, b) for a in specials_a for b in specials_b]
+    cases += [(rng.randrange(p), rng.randrange(two_p)) for _ in range(3000)]
+    # adversarial: limbs all-ones where allowed
+    for _ in range(500):
+        a = _val([rng.choice([0, M32, rng.getrandbits(32)]) for _ in range(8)]) % p
+        b = _val([rng.choice([0, M32, rng.getrandbits(32)]) for _ in range(8)]) % two_p
+        cases.append((a, b))
+    for a, b in cases:
+        r = mont_mul_model(a, b, p, np0)  # raises Overflow if a chain carries out
+        assert r < two_p
+        assert r % p == a * b * Rinv % p
+
+
+def test_lazy_add_sub_window():
+    """add_lazy/sub_lazy keep values in [0, 2p); BLS12-381 Fr needs the 2^256 carry (4p > 2^256)."""
+    F = po.BLS12_381_FR
+    p = F.p
+    assert 4 * p > 1 << 256 > 2 * p
+    rng = random.Random(7)
+    for _ in range(2000):
+        a, b = rng.randrange(2 * p), rng.randrange(2 * p)
+        t = a + b
+        carry, t256 = t >> 256, t & ((1 << 256) - 1)
+        d = (t256 - 2 * p) & ((1 << 256) - 1)
+        borrow = t256 < 2 * p
+        s = t256 if (borrow and not carry) else d
+        assert s < 2 * p and s % p == (a + b) % p
+        diff = (a - b) & ((1 << 256) - 1)
+        if a < b:
+            diff = (diff + 2 * p) & ((1 << 256) - 1)
+        assert diff < 2 * p and diff % p == (a - b) % p
