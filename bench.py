@@ -200,7 +200,7 @@ def run_ours(args):
     else:
         from ntt_b200.dist import FourStep
 
-        fs = FourStep(ctx, LOG_N, world, rank)
+        fs = FourStep(ctx, LOG_N, world, rank, fused=not args.no_fused)
         x_shard = c_oracle.splitmix_elements(n // world, p, 0x4E5454 + 100 + rank)
         fs.load_shard(torch.from_numpy(x_shard.view(np.int32)).cuda())
 
@@ -289,7 +289,8 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32x8 (256-bit modular integer)", "data": "synthetic",
         "config": {"workload": f"2^{LOG_N}-point forward NTT, {FIELD} (8x u32 limbs), in place, natural order in/out"
-                               + ("" if world == 1 else f", four-step over {world} GPUs with NCCL all-to-all"),
+                               + ("" if world == 1 else f", four-step over {world} GPUs, exchange = "
+                                  + ("NCCL all-to-all" if args.no_fused else "peer stores fused into the butterfly kernel (NVLink)")),
                    "field": FIELD, "log_n": LOG_N, "passes_per_step": passes,
                    "l2_policy": "input 512 MiB > 126 MB L2, no flush needed",
                    "binding_roofline": "int32-multiply pipe (see roofline_int); HBM is ~6x off"},
@@ -323,6 +324,7 @@ def main():
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--coalesce-bits", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of fused peer stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

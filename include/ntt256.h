@@ -95,6 +95,23 @@ int ntt256_fourstep_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, 
                           ntt256_stream stream);
 int ntt256_fourstep_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
                           ntt256_stream stream);
+/* step 1 with the exchange FUSED into its last pass: instead of storing the tile back in place,
+ * the butterfly kernel stores every output element straight into the receive buffer of its
+ * destination rank over NVLink.  peer_recv[s] = rank s's receive buffer (2^(log_n-log_p) elements)
+ * as mapped into THIS process (CUDA IPC / peer access; peer_recv[rank] is the local one).
+ * The caller only has to barrier before step 2 reads the receive buffer.  log_p <= 3. */
+int ntt256_fourstep_step1_peer(ntt256_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n, int log_r,
+                               int log_p, int rank, ntt256_stream stream);
+
+/* Exchange buffers for the fused step: cudaMalloc'ed by the library so that a CUDA IPC handle
+ * (64 bytes) describes exactly this buffer; the other ranks open it with THEIR device current. */
+int ntt256_ipc_alloc(int device, size_t bytes, void** d_ptr, unsigned char handle[64]);
+int ntt256_ipc_open(int device, const unsigned char handle[64], void** d_ptr);
+int ntt256_ipc_close(int device, void* d_ptr);
+int ntt256_ipc_free(int device, void* d_ptr);
+/* Lets kernels running on `device` store into memory of `peer_device` (NVLink peer access);
+ * needed once per peer before ntt256_fourstep_step1_peer.  Already-enabled is not an error. */
+int ntt256_enable_peer_access(int device, int peer_device);
 
 /* Introspection (host only, no CUDA call): JSON description of the pass plan that
  * ntt256_forward would run for 2^log_n points.  Returns the number of bytes needed

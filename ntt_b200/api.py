@@ -120,6 +120,16 @@ class Ntt256:
         self._check(self._L.ntt256_fourstep_step1(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))
         return shard
 
+    def fourstep_step1_peer(self, shard, peer_ptrs: Sequence[int], log_n: int, log_r: int, log_p: int, rank: int,
+                            stream=None):
+        """step 1 whose last pass stores straight into the peers' receive buffers (device pointers
+        valid in this process, one per rank)."""
+        ptr = _device_ptr(shard, 1 << (log_n - log_p))
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(v) for v in peer_ptrs])
+        self._check(self._L.ntt256_fourstep_step1_peer(self._h, ptr, arr, log_n, log_r, log_p, rank,
+                                                       _stream_handle(stream)))
+        return shard
+
     def fourstep_step2(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
         ptr = _device_ptr(shard, 1 << (log_n - log_p))
         self._check(self._L.ntt256_fourstep_step2(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))

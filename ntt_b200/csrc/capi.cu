@@ -48,7 +48,7 @@ struct ntt256_ctx {
   int hi_bits = 0, lo_bits = 0, loc_bits = 0;
   u32 c8[2][3][8];   // [direction][k-1] = w_8^(+-k)
   u32 w4[2][8];
-  int tile_bits = 10;
+  int tile_bits = 11;
   int coalesce_bits = 2;
   std::map<PlanKey, Plan> plans;
   void* d_stage = nullptr;
@@ -166,8 +166,13 @@ int get_plan(ntt256_ctx* ctx, const PlanKey& key, const Plan** out) {
   return NTT256_OK;
 }
 
+struct PeerSpec {
+  const void* const* ptrs = nullptr;
+  int bits = 0, shift = 0, rank = 0;
+};
+
 int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long batch_stride, int batch, bool inverse,
-             int scale_log_n, cudaStream_t stream) {
+             int scale_log_n, cudaStream_t stream, const PeerSpec* peer = nullptr) {
   PassArgs A;
   std::memset(&A, 0, sizeof(A));
   A.f = ctx->fp;
@@ -187,6 +192,12 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
   for (size_t i = 0; i < plan.passes.size(); ++i) {
     A.pd = plan.passes[i];
     if (scale_log_n >= 0 && i + 1 == plan.passes.size()) A.pd.scale_out = 1;
+    if (peer && i + 1 == plan.passes.size()) {
+      for (int r = 0; r < (1 << peer->bits); ++r) A.peer[r] = (unsigned long long)peer->ptrs[r];
+      A.peer_bits = peer->bits;
+      A.peer_shift = peer->shift;
+      A.peer_rank = peer->rank;
+    }
     const int T = A.pd.T;
     const unsigned threads = 1u << (T - 3);
     const size_t smem = (size_t)32 << T;
@@ -394,14 +405,29 @@ int ntt256_inverse_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_
 }
 
 static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log_r, int log_p, int rank,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const void* const* peer_recv = nullptr) {
   if (!ctx || !d_shard || log_n > ctx->max_log_n || !fourstep_args_ok(log_n, log_r, log_p, rank)) return NTT256_ERR_ARG;
   CTX_CUDA(cudaSetDevice(ctx->device));
   const Plan* plan = nullptr;
   // step 2 does not depend on the rank (no foreign time bits remain)
   int rc = get_plan(ctx, PlanKey{kind, log_n, log_r, log_p, kind == 1 ? rank : 0}, &plan);
   if (rc) return rc;
+  if (peer_recv && log_p > 0) {
+    if (log_p > 3) return NTT256_ERR_ARG;
+    PeerSpec ps;
+    ps.ptrs = peer_recv;
+    ps.bits = log_p;
+    ps.shift = log_n - 2 * log_p;  // local index bits below the destination-rank field
+    ps.rank = rank;
+    return run_plan(ctx, *plan, d_shard, 0, 1, false, -1, stream, &ps);
+  }
   return run_plan(ctx, *plan, d_shard, 0, 1, false, -1, stream);
+}
+
+int ntt256_fourstep_step1_peer(ntt256_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n, int log_r,
+                               int log_p, int rank, ntt256_stream stream) {
+  if (!peer_recv) return NTT256_ERR_ARG;
+  return fourstep(ctx, 1, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream, peer_recv);
 }
 
 int ntt256_fourstep_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
@@ -411,6 +437,54 @@ int ntt256_fourstep_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, 
 int ntt256_fourstep_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
                           ntt256_stream stream) {
   return fourstep(ctx, 2, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream);
+}
+
+int ntt256_ipc_alloc(int device, size_t bytes, void** d_ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!d_ptr || !handle || !bytes) return NTT256_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return NTT256_ERR_CUDA;
+  if (cudaMalloc(d_ptr, bytes) != cudaSuccess) return NTT256_ERR_NOMEM;
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, *d_ptr) != cudaSuccess) {
+    cudaFree(*d_ptr);
+    *d_ptr = nullptr;
+    return NTT256_ERR_CUDA;
+  }
+  std::memcpy(handle, &h, 64);
+  return NTT256_OK;
+}
+
+int ntt256_ipc_open(int device, const unsigned char handle[64], void** d_ptr) {
+  if (!d_ptr || !handle) return NTT256_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return NTT256_ERR_CUDA;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  // opened with the CONSUMER's device current: the mapping is a peer mapping usable by its kernels
+  if (cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return NTT256_ERR_CUDA;
+  return NTT256_OK;
+}
+
+int ntt256_ipc_close(int device, void* d_ptr) {
+  if (cudaSetDevice(device) != cudaSuccess) return NTT256_ERR_CUDA;
+  return cudaIpcCloseMemHandle(d_ptr) == cudaSuccess ? NTT256_OK : NTT256_ERR_CUDA;
+}
+
+int ntt256_ipc_free(int device, void* d_ptr) {
+  if (cudaSetDevice(device) != cudaSuccess) return NTT256_ERR_CUDA;
+  return cudaFree(d_ptr) == cudaSuccess ? NTT256_OK : NTT256_ERR_CUDA;
+}
+
+int ntt256_enable_peer_access(int device, int peer_device) {
+  if (device == peer_device) return NTT256_OK;
+  int can = 0;
+  if (cudaSetDevice(device) != cudaSuccess) return NTT256_ERR_CUDA;
+  if (cudaDeviceCanAccessPeer(&can, device, peer_device) != cudaSuccess || !can) return NTT256_ERR_CUDA;
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return NTT256_OK;
+  }
+  return e == cudaSuccess ? NTT256_OK : NTT256_ERR_CUDA;
 }
 
 size_t ntt256_plan_describe(int log_n, int max_log_n, int tile_bits, int coalesce_bits, char* buf, size_t buf_len) {

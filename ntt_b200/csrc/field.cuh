@@ -45,9 +45,11 @@ struct Fe {
 NTT_DEV void mul_row(u32* acc, const u32* a, u32 b) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    asm("mul.lo.u32 %0, %2, %3;\n\t"
-        "mul.hi.u32 %1, %2, %3;"
-        : "=&r"(acc[2 * j]), "=r"(acc[2 * j + 1])
+    // one plain IMAD.WIDE.U32 (full rate); mul.lo + mul.hi would be emitted as IMAD + IMAD.HI
+    asm("{\n\t.reg .u64 t;\n\t"
+        "mul.wide.u32 t, %2, %3;\n\t"
+        "mov.b64 {%0, %1}, t;\n\t}"
+        : "=r"(acc[2 * j]), "=r"(acc[2 * j + 1])
         : "r"(a[2 * j]), "r"(b));
   }
 }

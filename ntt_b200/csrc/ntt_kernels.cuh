@@ -32,6 +32,13 @@ struct PassArgs {
   u32 c8[3][8];        // w_8^1, w_8^2, w_8^3 (or their inverses), Montgomery form
   u32 scale[8];        // 1/n in Montgomery form (used when pd.scale_out)
   unsigned long long batch_stride;  // elements between consecutive transforms of a batch
+  // Fused exchange (multi-GPU four-step, last pass of step 1): when peer_bits > 0 the tile is
+  // not stored back in place but straight into the receive buffers of the destination ranks
+  // over NVLink (peer-mapped pointers): destination = top peer_bits of the local output index,
+  // remote index = (my rank << peer_shift) | (low peer_shift bits).  The all-to-all becomes
+  // the store phase of the butterfly kernel.
+  unsigned long long peer[8];
+  int peer_bits, peer_shift, peer_rank, pad_;
 };
 
 // ---------------------------------------------------------------- element I/O
@@ -243,10 +250,22 @@ ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
       if (first) __syncthreads();
       const u32 g0 = deposit32(lam0, pd.out_pos, T);
       const u32 s0 = 1u << pd.out_pos[sb], s1 = 1u << pd.out_pos[sb + 1], s2 = 1u << pd.out_pos[sb + 2];
+      if (A.peer_bits == 0) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const u32 off = g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
-        st_global_256(gbase + 2 * (size_t)off, x[u]);
+        for (int u = 0; u < 8; ++u) {
+          const u32 off = g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+          st_global_256(gbase + 2 * (size_t)off, x[u]);
+        }
+      } else {
+        const u32 lowmask = (1u << A.peer_shift) - 1u;
+        const u32 mine = (u32)A.peer_rank << A.peer_shift;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          // full local output index: block part + in-tile part
+          const u32 off = (u32)base + g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+          uint4* dst = reinterpret_cast<uint4*>(A.peer[off >> A.peer_shift]) + 2 * (size_t)(mine | (off & lowmask));
+          st_global_256(dst, x[u]);
+        }
       }
     }
   }

@@ -61,31 +61,147 @@ def exchange_reference(step1_out: list[np.ndarray], world: int) -> list[np.ndarr
 
 
 class FourStep:
-    """Distributed forward NTT of 2^log_n points over `world` ranks (this process is `rank`)."""
+    """Distributed forward NTT of 2^log_n points over `world` ranks (this process is `rank`).
 
-    def __init__(self, ctx, log_n: int, world: int, rank: int, log_r: int | None = None, group=None):
+    fused=False: step 1, NCCL all_to_all_single, step 2.
+    fused=True : the exchange is the store phase of step 1's last kernel -- every output element
+                 goes straight into the destination rank's receive buffer over NVLink
+                 (peer-mapped memory shared through CUDA IPC); only a barrier separates the steps.
+    """
+
+    def __init__(self, ctx, log_n: int, world: int, rank: int, log_r: int | None = None, group=None,
+                 fused: bool = False):
         self.ctx, self.log_n, self.world, self.rank, self.group = ctx, log_n, world, rank, group
         self.log_p = _log2(world)
         self.log_r = default_log_r(log_n) if log_r is None else log_r
         if self.log_r < self.log_p or log_n - self.log_r < self.log_p:
             raise ValueError("both R and C must be multiples of the world size")
+        self.fused = bool(fused) and world > 1
         self.a = None
         self.b = None
+        self._peers = None  # [(ptrs of every rank's buffer a), (ptrs of every rank's buffer b)]
+        self._keep, self._owned, self._opened = [], [], []
 
     def load_shard(self, shard):
         """shard: CUDA tensor with this rank's (R x C/P) input, 32 bytes per element."""
         import torch
 
-        self.a = shard.contiguous().view(-1)
-        self.b = torch.empty_like(self.a)
+        if self.fused:
+            nbytes = shard.numel() * shard.element_size()
+            self._dev = shard.device.index
+            self.a, self._ha = self._ipc_buffer(nbytes, 0)
+            self.b, self._hb = self._ipc_buffer(nbytes, 1)
+            self._exchange_handles()
+            self.a.copy_(shard.contiguous().view(-1).view(torch.int32))
+            torch.cuda.synchronize()
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)
+        else:
+            self.a = shard.contiguous().view(-1)
+            self.b = torch.empty_like(self.a)
         return self
 
+    _MAGIC = 0x5A5A0000
+
+    def _ipc_buffer(self, nbytes, which):
+        """cudaMalloc'ed by the library (so one IPC handle describes it), viewed as a torch tensor.
+        The driver carves small cudaMalloc requests out of shared blocks, and an IPC handle always
+        maps the whole block: allocate at least 2 MiB so that the buffer IS the block, and stamp a
+        magic word that the peers verify after opening the handle."""
+        import ctypes
+
+        import torch
+
+        from .lib import Ntt256Error, lib
+
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        rc = lib().ntt256_ipc_alloc(self._dev, max(nbytes, 2 << 20), ctypes.byref(ptr), handle)
+        if rc:
+            raise Ntt256Error(rc, "ipc_alloc")
+        self._owned.append(ptr.value)
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4", "data": (ptr.value, False),
+                                        "version": 2, "strides": None}
+
+        raw = _Raw()
+        t = torch.as_tensor(raw, device=torch.device("cuda", self._dev))
+        assert t.data_ptr() == ptr.value
+        t[0] = self._MAGIC + 2 * self.rank + which
+        torch.cuda.synchronize()
+        self._keep.append(raw)
+        return t, handle.raw
+
+    def _exchange_handles(self):
+        import ctypes
+
+        import torch.distributed as dist
+
+        from .lib import Ntt256Error, lib
+
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (self._ha, self._hb), group=self.group)
+        ptrs = [[], []]
+        for r, pair in enumerate(everyone):
+            for k, h in enumerate(pair):
+                if r == self.rank:
+                    ptrs[k].append((self.a if k == 0 else self.b).data_ptr())
+                else:
+                    p = ctypes.c_void_p()
+                    rc = lib().ntt256_ipc_open(self._dev, h, ctypes.byref(p))
+                    if rc:
+                        raise Ntt256Error(rc, f"ipc_open of rank {r}'s buffer")
+                    self._opened.append(p.value)
+                    ptrs[k].append(p.value)
+                    if self._peek(p.value) != self._MAGIC + 2 * r + k:
+                        raise RuntimeError(f"IPC mapping of rank {r}'s buffer {k} does not start at the buffer")
+        self._peers = ptrs
+        self._cur = 0  # which buffer holds the input
+        dist.barrier(group=self.group)
+
+    def _peek(self, ptr):
+        import torch
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (ptr, False), "version": 2,
+                                        "strides": None}
+
+        return int(torch.as_tensor(_Raw(), device=torch.device("cuda", self._dev)).cpu()[0])
+
+    def close(self):
+        from .lib import lib
+
+        import torch
+
+        if self.fused and self._peers is not None:
+            torch.cuda.synchronize()
+            try:
+                import torch.distributed as dist
+
+                dist.barrier(group=self.group)
+            except Exception:
+                pass
+            for p in self._opened:
+                lib().ntt256_ipc_close(self._dev, p)
+            for p in self._owned:
+                lib().ntt256_ipc_free(self._dev, p)
+            self._opened, self._owned, self._peers = [], [], None
+            self.a = self.b = None
+
     def forward(self):
-        """step 1 -> all-to-all -> step 2.  The result shard is returned (and becomes the input of
-        the next call: buffers ping-pong)."""
+        """One distributed transform.  The result shard is returned (and becomes the input of the
+        next call: buffers ping-pong)."""
         import torch.distributed as dist
 
         ctx = self.ctx
+        if self.fused:
+            src, dst = (self.a, self.b) if self._cur == 0 else (self.b, self.a)
+            ctx.fourstep_step1_peer(src, self._peers[1 - self._cur], self.log_n, self.log_r, self.log_p, self.rank)
+            dist.barrier(group=self.group)  # every rank's stores have landed (stream-ordered NCCL kernel)
+            ctx.fourstep_step2(dst, self.log_n, self.log_r, self.log_p, self.rank)
+            self._cur = 1 - self._cur
+            return dst
         ctx.fourstep_step1(self.a, self.log_n, self.log_r, self.log_p, self.rank)
         if self.world > 1:
             dist.all_to_all_single(self.b, self.a, group=self.group)

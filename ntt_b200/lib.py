@@ -17,7 +17,8 @@ FIELD_BN254_FR, FIELD_BLS12_381_FR = 0, 1
 EXPORTS = [
     "ntt256_ctx_create", "ntt256_ctx_create_named", "ntt256_ctx_destroy", "ntt256_ctx_set_tuning",
     "ntt256_forward", "ntt256_inverse", "ntt256_forward_batch", "ntt256_inverse_batch",
-    "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2",
+    "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2", "ntt256_fourstep_step1_peer", "ntt256_enable_peer_access",
+    "ntt256_ipc_alloc", "ntt256_ipc_open", "ntt256_ipc_close", "ntt256_ipc_free",
     "ntt256_plan_describe", "ntt256_plan_describe_fourstep", "ntt256_launch_count", "ntt256_strerror", "ntt256_last_cuda_error",
     "ntt256_version",
 ]
@@ -53,6 +54,12 @@ def lib() -> ctypes.CDLL:
             getattr(L, name).argtypes = [vp, vp, vp, ci, ci]
         for name in ("ntt256_fourstep_step1", "ntt256_fourstep_step2"):
             getattr(L, name).argtypes = [vp, vp, ci, ci, ci, ci, vp]
+        L.ntt256_fourstep_step1_peer.argtypes = [vp, vp, ctypes.POINTER(vp), ci, ci, ci, ci, vp]
+        L.ntt256_enable_peer_access.argtypes = [ci, ci]
+        L.ntt256_ipc_alloc.argtypes = [ci, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
+        L.ntt256_ipc_open.argtypes = [ci, ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.ntt256_ipc_close.argtypes = [ci, vp]
+        L.ntt256_ipc_free.argtypes = [ci, vp]
         L.ntt256_plan_describe.argtypes = [ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]
         L.ntt256_plan_describe.restype = ctypes.c_size_t
         L.ntt256_plan_describe_fourstep.argtypes = [ci] * 8 + [ctypes.c_char_p, ctypes.c_size_t]
@@ -68,7 +75,7 @@ def lib() -> ctypes.CDLL:
     return _LIB
 
 
-def plan_describe(log_n: int, max_log_n: int, tile_bits: int = 10, coalesce_bits: int = 2) -> dict:
+def plan_describe(log_n: int, max_log_n: int, tile_bits: int = 11, coalesce_bits: int = 2) -> dict:
     """Host-only: the pass plan ntt256_forward would run (JSON -> dict)."""
     import json
 
@@ -80,7 +87,7 @@ def plan_describe(log_n: int, max_log_n: int, tile_bits: int = 10, coalesce_bits
 
 
 def plan_describe_fourstep(step: int, log_n: int, log_r: int, log_p: int, rank: int, max_log_n: int,
-                           tile_bits: int = 10, coalesce_bits: int = 2) -> dict:
+                           tile_bits: int = 11, coalesce_bits: int = 2) -> dict:
     """Host-only: the plan of local step 1 or 2 of the four-step decomposition on `rank`."""
     import json
 

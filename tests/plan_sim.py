@@ -19,7 +19,7 @@ def _brev(v: int, bits: int) -> int:
 
 
 def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inverse: bool = False,
-             scale: int | None = None) -> None:
+             scale: int | None = None, peer: dict | None = None) -> None:
     """In-place simulation of one pass over one transform (len(data) = 2^(T + nblk_bits))."""
     T, d = pd["T"], pd["d"]
     lowp = T - d
@@ -109,7 +109,12 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
                     for u in range(8):
                         stores.append((base + _deposit(lams[u], pd["out_pos"], T), x[u]))
             for pos, val in stores:
-                data[pos] = val
+                if peer is None:
+                    data[pos] = val
+                else:  # fused exchange: store into the destination rank's receive buffer
+                    dest = pos >> peer["shift"]
+                    roff = (peer["rank"] << peer["shift"]) | (pos & ((1 << peer["shift"]) - 1))
+                    peer["recv"][dest][roff] = val
 
 
 def run_plan(data: list[int], plan: dict, p: int, g: int, max_log_n: int, inverse: bool = False) -> list[int]:

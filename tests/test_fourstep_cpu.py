@@ -46,6 +46,31 @@ def test_fourstep_model_equals_oracle(built, log_n, log_r, world, T, g):
     assert got == want
 
 
+@pytest.mark.parametrize("log_n,log_r,world", [(8, 4, 2), (10, 5, 4), (11, 6, 8)])
+def test_fused_peer_store_equals_all_to_all(built, log_n, log_r, world):
+    """The store phase of step 1's last pass in peer mode (ntt256_fourstep_step1_peer) must put
+    every element exactly where step 1 + all-to-all would."""
+    F = po.BN254_FR
+    log_p = world.bit_length() - 1
+    rng = random.Random(3)
+    x = [rng.randrange(F.p) for _ in range(1 << log_n)]
+    shards = nd.scatter_input(co.ints_to_array(x), log_n, world, log_r)
+    w_max = pow(F.g, (F.p - 1) >> 12, F.p)
+    plain, recv = [], [[None] * (1 << (log_n - log_p)) for _ in range(world)]
+    for r, s in enumerate(shards):
+        plan = plan_describe_fourstep(1, log_n, log_r, log_p, r, 12, 6, 1)
+        a, b = co.array_to_ints(s), co.array_to_ints(s)
+        for i, pd in enumerate(plan["passes"]):
+            last = i == len(plan["passes"]) - 1
+            plan_sim.run_pass(a, pd, F.p, w_max, 12)
+            plan_sim.run_pass(b, pd, F.p, w_max, 12,
+                              peer={"shift": log_n - 2 * log_p, "rank": r, "recv": recv} if last else None)
+        plain.append(co.ints_to_array(a))
+    want = nd.exchange_reference(plain, world)
+    for r in range(world):
+        assert recv[r] == co.array_to_ints(want[r])
+
+
 def test_scatter_gather_are_inverse_views():
     log_n, world = 8, 4
     x = np.arange((1 << log_n) * 8, dtype=np.uint32).reshape(-1, 8)

@@ -320,3 +320,38 @@ def test_fourstep_ranks_emulated_on_one_gpu(torch_cuda, ctxs, log_n, world):
         torch.cuda.synchronize()
         s2.append(d.cpu().numpy().view(np.uint32).reshape(-1, 8))
     assert np.array_equal(nd.gather_output(s2, log_n, world, log_r), want)
+
+
+@pytest.mark.parametrize("log_n,world", [(14, 2), (16, 4), (20, 8)])
+def test_fused_peer_store_on_one_gpu(torch_cuda, ctxs, log_n, world):
+    """ntt256_fourstep_step1_peer with every rank's receive buffer on this GPU: the store phase of
+    the butterfly kernel must deliver exactly what step 1 + all-to-all delivers."""
+    from ntt_b200 import dist as nd
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bls12_381_fr"]
+    ctx = ctxs("bls12_381_fr", 24)
+    lp, lr = world.bit_length() - 1, nd.default_log_r(log_n)
+    x = co.splitmix_elements(1 << log_n, p, 99 + log_n)
+    shards = nd.scatter_input(x, log_n, world)
+    plain = []
+    for r in range(world):
+        d = torch.from_numpy(shards[r].view(np.int32)).cuda().view(-1)
+        ctx.fourstep_step1(d, log_n, lr, lp, r)
+        torch.cuda.synchronize()
+        plain.append(d.cpu().numpy().view(np.uint32).reshape(-1, 8))
+    want = nd.exchange_reference(plain, world)
+    recv = [torch.zeros(8 << (log_n - lp), dtype=torch.int32, device="cuda") for _ in range(world)]
+    for r in range(world):
+        d = torch.from_numpy(shards[r].view(np.int32)).cuda().view(-1)
+        ctx.fourstep_step1_peer(d, [t.data_ptr() for t in recv], log_n, lr, lp, r)
+    torch.cuda.synchronize()
+    outs = []
+    for r in range(world):
+        assert np.array_equal(recv[r].cpu().numpy().view(np.uint32).reshape(-1, 8), want[r])
+        ctx.fourstep_step2(recv[r], log_n, lr, lp, r)
+        torch.cuda.synchronize()
+        outs.append(recv[r].cpu().numpy().view(np.uint32).reshape(-1, 8))
+    assert np.array_equal(nd.gather_output(outs, log_n, world, lr), co.ntt(x, p, g, threads=8))

@@ -21,17 +21,24 @@ torch.cuda.set_device(lr_)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
 p, g = FIELDS["bls12_381_fr"]
 ctx = Ntt256("bls12_381_fr", max_log_n=22, device=lr_)
-for log_n in (14, 20):
+for fused in (False, True):
+  for log_n in (14, 20):
     x = co.splitmix_elements(1 << log_n, p, 99 + log_n)          # same on every rank
     shard = nd.scatter_input(x, log_n, world)[rank]
-    fs = nd.FourStep(ctx, log_n, world, rank).load_shard(torch.from_numpy(shard.view(np.int32)).cuda())
-    out = fs.forward()
+    fs = nd.FourStep(ctx, log_n, world, rank, fused=fused).load_shard(torch.from_numpy(shard.view(np.int32)).cuda().view(-1))
+    out = fs.forward().clone()
     torch.cuda.synchronize()
     gathered = [torch.empty_like(out) for _ in range(world)]
     dist.all_gather(gathered, out)
     if rank == 0:
         X = nd.gather_output([t.cpu().numpy().view(np.uint32).reshape(-1, 8) for t in gathered], log_n, world)
-        assert np.array_equal(X, co.ntt(x, p, g, threads=8)), f"four-step 2^{log_n} over {world} GPUs differs from the oracle"
+        assert np.array_equal(X, co.ntt(x, p, g, threads=8)), f"four-step 2^{log_n} over {world} GPUs (fused={fused}) differs from the oracle"
+    # second call reuses the ping-pong buffers: transform of the previous output
+    out2 = fs.forward().clone()
+    torch.cuda.synchronize()
+    dist.barrier()
+    if fused:
+        fs.close()
 # batch sharding: independent transforms, no collective
 batch, log_n = 16, 12
 lo, hi = nd.shard_batch(batch, world, rank)
