@@ -28,8 +28,10 @@ constexpr int kLocBitsMax = 12;
 struct PlanKey {
   int kind;  // 0 = whole transform, 1 = four-step step 1, 2 = four-step step 2
   int log_n, log_r, log_p, rank;
+  int tile_bits = 0;  // 0 = the context's tile_bits
   bool operator<(const PlanKey& o) const {
-    return std::tie(kind, log_n, log_r, log_p, rank) < std::tie(o.kind, o.log_n, o.log_r, o.log_p, o.rank);
+    return std::tie(kind, log_n, log_r, log_p, rank, tile_bits) <
+           std::tie(o.kind, o.log_n, o.log_r, o.log_p, o.rank, o.tile_bits);
   }
 };
 
@@ -50,6 +52,8 @@ struct ntt256_ctx {
   u32 w4[2][8];
   int tile_bits = 11;
   int coalesce_bits = 2;
+  bool auto_tile = true;                  // shrink the tile for small problems so the grid fills the chip
+  std::map<int, uint4*> loc_scaled;       // log_n -> (1/n) * loc[] : folds the inverse scaling into a round twiddle
   std::map<PlanKey, Plan> plans;
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
@@ -157,7 +161,8 @@ bool fourstep_args_ok(int log_n, int log_r, int log_p, int rank) {
 int get_plan(ntt256_ctx* ctx, const PlanKey& key, const Plan** out) {
   auto it = ctx->plans.find(key);
   if (it == ctx->plans.end()) {
-    PlanRequest req = build_request(key, ctx->tile_bits, ctx->coalesce_bits, ctx->max_log_n);
+    PlanRequest req =
+        build_request(key, key.tile_bits ? key.tile_bits : ctx->tile_bits, ctx->coalesce_bits, ctx->max_log_n);
     Plan plan;
     if (!make_plan(req, &plan)) return NTT256_ERR_PLAN;
     it = ctx->plans.emplace(key, plan).first;
@@ -185,13 +190,42 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
   A.inverse = inverse ? 1 : 0;
   std::memcpy(A.c8, ctx->c8[inverse ? 1 : 0], sizeof(A.c8));
   A.batch_stride = batch_stride;
+  A.scaled_round = -1;
+  const uint4* loc_scaled = nullptr;
   if (scale_log_n >= 0) {
     U256 nm = ctx->hf.to_mont(u256_small(1ull << scale_log_n));
-    to_u32(ctx->hf.inv(nm), A.scale);
+    U256 ninv = ctx->hf.inv(nm);
+    to_u32(ninv, A.scale);
+    if (plan.passes.back().nrounds >= 2) {
+      // fold 1/n into the twiddle table of the last pass's first round (all 8 elements of that
+      // round are multiplied, the trivial one by (1/n)*R instead of being skipped)
+      auto it = ctx->loc_scaled.find(scale_log_n);
+      if (it == ctx->loc_scaled.end()) {
+        uint4* tab = nullptr;
+        const unsigned long long count = 1ull << ctx->loc_bits;
+        CTX_CUDA(cudaMalloc((void**)&tab, count * 32));
+        Fe c;
+        to_u32(ninv, c.v);
+        table_scale_kernel<<<(unsigned)((count + 127) / 128), 128, 0, stream>>>(tab, ctx->loc, count, ctx->fp, c);
+        ++ctx->launches;
+        CTX_CUDA(cudaGetLastError());
+        it = ctx->loc_scaled.emplace(scale_log_n, tab).first;
+      }
+      loc_scaled = it->second;
+    }
   }
   for (size_t i = 0; i < plan.passes.size(); ++i) {
     A.pd = plan.passes[i];
-    if (scale_log_n >= 0 && i + 1 == plan.passes.size()) A.pd.scale_out = 1;
+    A.scaled_round = -1;
+    A.loc_scaled = nullptr;
+    if (scale_log_n >= 0 && i + 1 == plan.passes.size()) {
+      if (loc_scaled) {
+        A.scaled_round = 0;
+        A.loc_scaled = loc_scaled;
+      } else {
+        A.pd.scale_out = 1;
+      }
+    }
     if (peer && i + 1 == plan.passes.size()) {
       for (int r = 0; r < (1 << peer->bits); ++r) A.peer[r] = (unsigned long long)peer->ptrs[r];
       A.peer_bits = peer->bits;
@@ -235,8 +269,20 @@ int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse,
   if (!ctx || !d_data || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
   CTX_CUDA(cudaSetDevice(ctx->device));
   if (log_n < 3) return run_tiny(ctx, d_data, log_n, (unsigned long long)batch, inverse, stream);
+  // Tile choice: 2^tile_bits elements per CTA is best when the grid is large; small problems
+  // get smaller tiles so that at least ~2 CTAs per SM exist (a 2^16 transform is 32 tiles of 2^11).
+  int tile = 0;
+  if (ctx->auto_tile) {
+    const long long want_ctas = 2 * 148;
+    tile = ctx->tile_bits;
+    while (tile > 8 && tile > 3 && (((long long)batch << log_n) >> tile) < want_ctas) --tile;
+    if (tile > log_n) tile = log_n;
+    if (tile == ctx->tile_bits) tile = 0;
+  }
   const Plan* plan = nullptr;
-  int rc = get_plan(ctx, PlanKey{0, log_n, 0, 0, 0}, &plan);
+  PlanKey key{0, log_n, 0, 0, 0};
+  key.tile_bits = tile;
+  int rc = get_plan(ctx, key, &plan);
   if (rc) return rc;
   // batches larger than one grid dimension are issued in slices
   const int kSlice = 65535;
@@ -371,6 +417,7 @@ void ntt256_ctx_destroy(ntt256_ctx* ctx) {
   if (ctx->om_hi) cudaFree(ctx->om_hi);
   if (ctx->om_lo) cudaFree(ctx->om_lo);
   if (ctx->loc) cudaFree(ctx->loc);
+  for (auto& kv : ctx->loc_scaled) cudaFree(kv.second);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   delete ctx;
 }
@@ -381,6 +428,7 @@ int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits) {
     return NTT256_ERR_ARG;
   ctx->tile_bits = tile_bits;
   ctx->coalesce_bits = coalesce_bits;
+  ctx->auto_tile = false;
   ctx->plans.clear();
   return NTT256_OK;
 }

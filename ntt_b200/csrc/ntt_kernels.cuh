@@ -38,7 +38,11 @@ struct PassArgs {
   // remote index = (my rank << peer_shift) | (low peer_shift bits).  The all-to-all becomes
   // the store phase of the butterfly kernel.
   unsigned long long peer[8];
-  int peer_bits, peer_shift, peer_rank, pad_;
+  int peer_bits, peer_shift, peer_rank;
+  // Inverse NTT: round `scaled_round` of this pass reads its twiddles from loc_scaled = (1/n)*loc
+  // and multiplies all 8 elements (also the one whose twiddle is 1), which applies the 1/n.
+  int scaled_round;
+  const uint4* loc_scaled;
 };
 
 // ---------------------------------------------------------------- element I/O
@@ -182,6 +186,8 @@ ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
       const u32 tl_mask = (1u << (pb - lowp)) - 1u;
       const u32 tl0 = (lam0 >> lowp) & tl_mask;
       const int ush = sb - lowp;         // >= 0 here (only the last round can dip below)
+      const bool scaled = (r == A.scaled_round);
+      const uint4* loc_tab = scaled ? A.loc_scaled : A.loc;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         // v = bit-reversed processed bits of u; tau_lo includes the group's unprocessed bits
@@ -189,13 +195,13 @@ ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
         if (nb == 3) { v = ((u & 4) >> 2) | (u & 2) | ((u & 1) << 2); rest = 0; }
         else if (nb == 2) { v = ((u >> 2) & 1) | (((u >> 1) & 1) << 1); rest = u & 1; }
         else { v = (u >> 2) & 1; rest = u & 3; }
-        if (nb == 3 ? (u != 0) : (nb == 2 ? ((u >> 1) != 0) : ((u >> 2) != 0))) {
+        if (scaled || (nb == 3 ? (u != 0) : (nb == 2 ? ((u >> 1) != 0) : ((u >> 2) != 0)))) {
           const u32 tl = (tl0 | (rest << ush)) & tl_mask;
           u32 e = (tl * v) << sh;
           if (A.inverse) e = (0u - e);
           e &= (1u << A.loc_bits) - 1u;
           u32 w[8];
-          ld_table(w, A.loc, e);
+          ld_table(w, loc_tab, e);
           mul_by(x[u], w, f);
         }
       }

@@ -110,6 +110,9 @@ struct Search {
         }
       }
     }
+    // pad the tile with the lowest free positions (pure passengers): a tile below T bits means
+    // a CTA with idle lanes and shorter contiguous runs, never less work
+    for (int p = 0; p < c.nbits && (int)S.size() < c.T; ++p) add(p);
     std::sort(S.begin(), S.end());
     // placement
     std::vector<int> nl(lab);

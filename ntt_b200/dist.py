@@ -156,7 +156,10 @@ class FourStep:
                     ptrs[k].append(p.value)
                     if self._peek(p.value) != self._MAGIC + 2 * r + k:
                         raise RuntimeError(f"IPC mapping of rank {r}'s buffer {k} does not start at the buffer")
+        import torch
+
         self._peers = ptrs
+        self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", self._dev))
         self._cur = 0  # which buffer holds the input
         dist.barrier(group=self.group)
 
@@ -198,7 +201,10 @@ class FourStep:
         if self.fused:
             src, dst = (self.a, self.b) if self._cur == 0 else (self.b, self.a)
             ctx.fourstep_step1_peer(src, self._peers[1 - self._cur], self.log_n, self.log_r, self.log_p, self.rank)
-            dist.barrier(group=self.group)  # every rank's stores have landed (stream-ordered NCCL kernel)
+            # stream-ordered barrier without blocking the host: a 1-element all-reduce completes on a
+            # rank only after every rank's NCCL kernel has started, i.e. after every rank's step-1
+            # kernel (and its peer stores) has finished
+            dist.all_reduce(self._flag, group=self.group)
             ctx.fourstep_step2(dst, self.log_n, self.log_r, self.log_p, self.rank)
             self._cur = 1 - self._cur
             return dst

@@ -89,10 +89,13 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
                         uproc = u >> (3 - nb)
                         v = _brev(uproc, nb)
                         rest = u & ((1 << (3 - nb)) - 1)
-                        if uproc != 0:
+                        fold = scale is not None and pd.get("scaled_round", -1) == r
+                        if uproc != 0 or fold:
                             tl = (tl0 | (rest << ush)) & tl_mask
                             e = ((tl * v) << sh) & ((1 << loc_bits) - 1)
                             x[u] = x[u] * root(e * (N >> loc_bits)) % p
+                            if fold:
+                                x[u] = x[u] * scale % p
                     for u in range(8):
                         tile[lams[u]] = x[u]
                 else:
@@ -126,7 +129,10 @@ def run_plan(data: list[int], plan: dict, p: int, g: int, max_log_n: int, invers
         pd = dict(pd)
         scale = None
         if inverse and i == len(passes) - 1:
-            pd["scale_out"] = 1
             scale = pow(n, p - 2, p)
+            if pd["nrounds"] >= 2:
+                pd["scaled_round"] = 0  # 1/n folded into the first round's twiddle table
+            else:
+                pd["scale_out"] = 1
         run_pass(out, pd, p, w_max, max_log_n, inverse, scale)
     return out
