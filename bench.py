@@ -325,7 +325,10 @@ def run_ours(args):
         "roofline_int": {"bound": "int32-mul", "achieved": int_achieved / 1e12, "peak": int_peak_macs / 1e12,
                          "unit": "T wide-MAC/s", "frac": int_achieved / int_peak_macs,
                          "work": "136 MACs x (n/2) log2 n modmuls (SURVEY 8d)",
-                         "peak_source": "measured IMAD.WIDE.U32 rate, profiles/r01_microbench_pipes.jsonl"},
+                         "peak_source": "measured plain IMAD.WIDE.U32 rate, profiles/r01_microbench_pipes.jsonl",
+                         "carry_chain_peak": 9.2, "frac_of_carry_chain_peak": int_achieved / 9.2e12,
+                         "note": "256-bit products need carry-predicate IMAD.WIDE forms, which run at half rate on "
+                                 "B200 (9.2 T/s): profiles/r01_microbench_notes.md"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
     }
     if world == 1 and not args.no_cpu_baseline:
