@@ -355,3 +355,47 @@ def test_fused_peer_store_on_one_gpu(torch_cuda, ctxs, log_n, world):
         torch.cuda.synchronize()
         outs.append(recv[r].cpu().numpy().view(np.uint32).reshape(-1, 8))
     assert np.array_equal(nd.gather_output(outs, log_n, world, lr), co.ntt(x, p, g, threads=8))
+
+
+def test_small_contexts_and_huge_batches(torch_cuda):
+    """Contexts whose tables are smaller than the defaults (max_log_n < 12: short round-twiddle
+    table) and batches beyond one grid dimension (65535) must work."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    for max_log_n in (1, 2, 3, 5, 8, 11):
+        ctx = Ntt256("bn254_fr", max_log_n=max_log_n)
+        for log_n in range(0, max_log_n + 1):
+            x = co.splitmix_elements(3 << log_n, p, 17 * max_log_n + log_n)
+            got = _gpu_forward(torch, ctx, x, log_n, batch=3)
+            for b in range(3):
+                assert np.array_equal(got[b << log_n:(b + 1) << log_n], co.ntt(x[b << log_n:(b + 1) << log_n], p, g)), (max_log_n, log_n)
+            assert np.array_equal(_gpu_forward(torch, ctx, got, log_n, batch=3, inverse=True), x)
+        ctx.close()
+    ctx = Ntt256("bn254_fr", max_log_n=8)
+    batch, log_n = 70000, 3
+    x = co.splitmix_elements(batch << log_n, p, 5)
+    got = _gpu_forward(torch, ctx, x, log_n, batch=batch)
+    for b in (0, 1, 65534, 65535, 65536, 69999):
+        assert np.array_equal(got[b << log_n:(b + 1) << log_n], co.ntt(x[b << log_n:(b + 1) << log_n], p, g)), b
+    assert np.array_equal(_gpu_forward(torch, ctx, got, log_n, batch=batch, inverse=True), x)
+    ctx.close()
+
+
+def test_montgomery_form_data_is_transparent(torch_cuda, ctxs):
+    """The transform is linear, so data kept in Montgomery form (x*R mod p, what most prover
+    stacks store) goes through the same entry points unchanged: NTT(xR) = R*NTT(x)."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    p, g = FIELDS["bls12_381_fr"]
+    R = (1 << 256) % p
+    ctx = ctxs("bls12_381_fr", 20)
+    log_n = 13
+    vals = co.array_to_ints(co.splitmix_elements(1 << log_n, p, 77))
+    xm = co.ints_to_array([v * R % p for v in vals])
+    got = co.array_to_ints(_gpu_forward(torch_cuda, ctx, xm, log_n))
+    want = co.array_to_ints(co.ntt(co.ints_to_array(vals), p, g, threads=4))
+    assert got == [v * R % p for v in want]
