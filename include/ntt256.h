@@ -75,10 +75,31 @@ int ntt256_forward_batch(ntt256_ctx* ctx, void* d_data, int log_n, int batch, nt
 int ntt256_inverse_batch(ntt256_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream);
 
 /* Reference-like synchronous convenience: HOST buffer in, HOST buffer out (may alias), the
- * library stages through its own device buffer: H2D, transform, D2H, synchronise.
+ * library stages through its own device buffer: H2D, transform, D2H, synchronise.  Batches are
+ * streamed in chunks (uplink, kernels and downlink overlap; pass pinned memory for that).
  * Mirrors main() of big-num.cu:424-460 (cudaMemcpy H2D, NTT_GZKP, cudaMemcpy D2H). */
 int ntt256_forward_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch);
 int ntt256_inverse_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch);
+
+/* ---- companions of the transform (SURVEY.md par. 8f: the prover steps either side of an NTT;
+ * the reference has none of them -- its kernels were lifted out of that context,
+ * /root/reference/src/GZKP-NTT.cu:321-386).  All on device memory, asynchronous on `stream`.
+ *
+ * Element-wise product of two arrays of n elements.  mont_form = 0: canonical residues in and out
+ * (out = a*b mod p); mont_form = 1: Montgomery-form data in and out (out = a*b*2^-256 mod p, i.e.
+ * the Montgomery product, one multiplication instead of two).  d_out may alias d_a or d_b. */
+int ntt256_vec_mul(ntt256_ctx* ctx, void* d_out, const void* d_a, const void* d_b, unsigned long long n, int mont_form,
+                   ntt256_stream stream);
+/* In-place conversion of n elements to / from Montgomery form (x*2^256 mod p).  The transforms
+ * themselves are linear and therefore work on Montgomery-form data unchanged. */
+int ntt256_to_montgomery(ntt256_ctx* ctx, void* d_data, unsigned long long n, ntt256_stream stream);
+int ntt256_from_montgomery(ntt256_ctx* ctx, void* d_data, unsigned long long n, ntt256_stream stream);
+/* Coset transforms: forward X[k] = sum_j (shift^j * x[j]) * w_n^(jk); inverse is its exact
+ * inverse (x[j] = shift^-j * INTT(X)[j]).  shift: 8 LE u32 limbs, 0 < shift < p. */
+int ntt256_coset_forward(ntt256_ctx* ctx, void* d_data, int log_n, int batch, const uint32_t shift[8],
+                         ntt256_stream stream);
+int ntt256_coset_inverse(ntt256_ctx* ctx, void* d_data, int log_n, int batch, const uint32_t shift[8],
+                         ntt256_stream stream);
 
 /* Multi-GPU four-step pieces (SURVEY.md par. 8e).  One process per GPU; the all-to-all between
  * the two calls is done by the caller (torch.distributed / NCCL, see ntt_b200/dist.py).

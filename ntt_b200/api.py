@@ -115,6 +115,35 @@ class Ntt256:
         self._check(self._L.ntt256_inverse_batch(self._h, ptr, log_n, batch, _stream_handle(stream)))
         return data
 
+    # ---- companions (SURVEY.md par. 8f)
+    def vec_mul(self, a, b, out=None, mont_form: bool = False, stream=None):
+        """out = a*b element-wise (canonical data) or the Montgomery product (mont_form=True)."""
+        n = a.numel() * a.element_size() // 32
+        out = a if out is None else out
+        pa, pb, po = _device_ptr(a, n), _device_ptr(b, n), _device_ptr(out, n)
+        self._check(self._L.ntt256_vec_mul(self._h, po, pa, pb, n, int(mont_form), _stream_handle(stream)))
+        return out
+
+    def to_montgomery(self, data, stream=None):
+        n = data.numel() * data.element_size() // 32
+        self._check(self._L.ntt256_to_montgomery(self._h, _device_ptr(data, n), n, _stream_handle(stream)))
+        return data
+
+    def from_montgomery(self, data, stream=None):
+        n = data.numel() * data.element_size() // 32
+        self._check(self._L.ntt256_from_montgomery(self._h, _device_ptr(data, n), n, _stream_handle(stream)))
+        return data
+
+    def coset_forward(self, data, log_n: int, shift: int, batch: int = 1, stream=None):
+        ptr = _device_ptr(data, batch << log_n)
+        self._check(self._L.ntt256_coset_forward(self._h, ptr, log_n, batch, _u32p(_limbs(shift)), _stream_handle(stream)))
+        return data
+
+    def coset_inverse(self, data, log_n: int, shift: int, batch: int = 1, stream=None):
+        ptr = _device_ptr(data, batch << log_n)
+        self._check(self._L.ntt256_coset_inverse(self._h, ptr, log_n, batch, _u32p(_limbs(shift)), _stream_handle(stream)))
+        return data
+
     def fourstep_step1(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
         ptr = _device_ptr(shard, 1 << (log_n - log_p))
         self._check(self._L.ntt256_fourstep_step1(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))

@@ -54,6 +54,15 @@ struct ntt256_ctx {
   int coalesce_bits = 2;
   bool auto_tile = true;                  // shrink the tile for small problems so the grid fills the chip
   std::map<int, uint4*> loc_scaled;       // log_n -> (1/n) * loc[] : folds the inverse scaling into a round twiddle
+  struct CosetTables {
+    U256 shift;
+    int log_n, lo_bits;
+    uint4 *hi, *lo;
+  };
+  std::vector<CosetTables> cosets;        // small cache of shift^j tables (forward and inverse shifts)
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // pipelined host batches
+  cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_done[3] = {nullptr, nullptr, nullptr},
+              ev_out[3] = {nullptr, nullptr, nullptr};
   std::map<PlanKey, Plan> plans;
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
@@ -295,10 +304,7 @@ int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse,
   return NTT256_OK;
 }
 
-int transform_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch, bool inverse) {
-  if (!ctx || !h_in || !h_out || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
-  CTX_CUDA(cudaSetDevice(ctx->device));
-  const size_t bytes = ((size_t)batch << log_n) * 32;
+int ensure_stage(ntt256_ctx* ctx, size_t bytes) {
   if (bytes > ctx->stage_bytes) {
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     ctx->d_stage = nullptr;
@@ -306,11 +312,101 @@ int transform_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, in
     CTX_CUDA(cudaMalloc(&ctx->d_stage, bytes));
     ctx->stage_bytes = bytes;
   }
-  CTX_CUDA(cudaMemcpyAsync(ctx->d_stage, h_in, bytes, cudaMemcpyHostToDevice, 0));
-  int rc = transform(ctx, ctx->d_stage, log_n, batch, inverse, 0);
+  return NTT256_OK;
+}
+
+// Host buffers in, host buffers out.  A single transform is H2D -> passes -> D2H.  A batch is
+// cut into chunks that flow through a 3-slot ring on three streams, so the PCIe uplink, the
+// kernels and the downlink work on different chunks at the same time (pinned host memory is
+// needed for the copies to be asynchronous; pageable memory still gives correct results).
+int transform_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch, bool inverse) {
+  if (!ctx || !h_in || !h_out || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  const size_t one = ((size_t)1 << log_n) * 32;
+  const size_t bytes = one * batch;
+  const size_t kChunkBytes = (size_t)32 << 20;
+  int per_chunk = (int)std::max<size_t>(1, kChunkBytes / one);
+  if (batch < 2 * per_chunk || batch < 4) {
+    int rc = ensure_stage(ctx, bytes);
+    if (rc) return rc;
+    CTX_CUDA(cudaMemcpyAsync(ctx->d_stage, h_in, bytes, cudaMemcpyHostToDevice, 0));
+    rc = transform(ctx, ctx->d_stage, log_n, batch, inverse, 0);
+    if (rc) return rc;
+    CTX_CUDA(cudaMemcpyAsync(h_out, ctx->d_stage, bytes, cudaMemcpyDeviceToHost, 0));
+    CTX_CUDA(cudaStreamSynchronize(0));
+    return NTT256_OK;
+  }
+  if (!ctx->s_h2d) {
+    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) {
+      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t slot_bytes = one * per_chunk;
+  int rc = ensure_stage(ctx, 3 * slot_bytes);
   if (rc) return rc;
-  CTX_CUDA(cudaMemcpyAsync(h_out, ctx->d_stage, bytes, cudaMemcpyDeviceToHost, 0));
-  CTX_CUDA(cudaStreamSynchronize(0));
+  cudaStream_t s_comp = ctx->s_comp;
+  const int nchunks = (batch + per_chunk - 1) / per_chunk;
+  for (int c = 0; c < nchunks; ++c) {
+    const int slot = c % 3;
+    const int b0 = c * per_chunk, nb = std::min(per_chunk, batch - b0);
+    char* d = (char*)ctx->d_stage + slot * slot_bytes;
+    if (c >= 3) CTX_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_out[slot], 0));  // slot drained
+    CTX_CUDA(cudaMemcpyAsync(d, (const char*)h_in + (size_t)b0 * one, (size_t)nb * one, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CTX_CUDA(cudaEventRecord(ctx->ev_in[slot], ctx->s_h2d));
+    CTX_CUDA(cudaStreamWaitEvent(s_comp, ctx->ev_in[slot], 0));
+    rc = transform(ctx, d, log_n, nb, inverse, s_comp);
+    if (rc) return rc;
+    CTX_CUDA(cudaEventRecord(ctx->ev_done[slot], s_comp));
+    CTX_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[slot], 0));
+    CTX_CUDA(cudaMemcpyAsync((char*)h_out + (size_t)b0 * one, d, (size_t)nb * one, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CTX_CUDA(cudaEventRecord(ctx->ev_out[slot], ctx->s_d2h));
+  }
+  CTX_CUDA(cudaStreamSynchronize(ctx->s_d2h));
+  CTX_CUDA(cudaStreamSynchronize(s_comp));
+  return NTT256_OK;
+}
+
+int get_coset_tables(ntt256_ctx* ctx, const U256& shift_plain, int log_n, const ntt256_ctx::CosetTables** out) {
+  for (auto& c : ctx->cosets)
+    if (c.log_n == log_n && u256_cmp(c.shift, shift_plain) == 0) {
+      *out = &c;
+      return NTT256_OK;
+    }
+  if (ctx->cosets.size() >= 8) {
+    cudaFree(ctx->cosets.front().hi);
+    cudaFree(ctx->cosets.front().lo);
+    ctx->cosets.erase(ctx->cosets.begin());
+  }
+  ntt256_ctx::CosetTables t;
+  t.shift = shift_plain;
+  t.log_n = log_n;
+  t.lo_bits = log_n / 2;
+  t.hi = t.lo = nullptr;
+  U256 sm = ctx->hf.to_mont(shift_plain);
+  int rc = build_power_table(ctx, &t.lo, sm, t.lo_bits);
+  if (rc) return rc;
+  rc = build_power_table(ctx, &t.hi, pow2k(ctx->hf, sm, t.lo_bits), log_n - t.lo_bits);
+  if (rc) return rc;
+  ctx->cosets.push_back(t);
+  *out = &ctx->cosets.back();
+  return NTT256_OK;
+}
+
+int coset_scale(ntt256_ctx* ctx, void* d_data, int log_n, int batch, const U256& shift_plain, cudaStream_t stream) {
+  const ntt256_ctx::CosetTables* t = nullptr;
+  int rc = get_coset_tables(ctx, shift_plain, log_n, &t);
+  if (rc) return rc;
+  const unsigned long long n = (unsigned long long)batch << log_n;
+  const int threads = 128;
+  coset_scale_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>((uint4*)d_data, n, log_n, t->lo_bits,
+                                                                                      t->hi, t->lo, ctx->fp);
+  ++ctx->launches;
+  CTX_CUDA(cudaGetLastError());
   return NTT256_OK;
 }
 
@@ -418,6 +514,18 @@ void ntt256_ctx_destroy(ntt256_ctx* ctx) {
   if (ctx->om_lo) cudaFree(ctx->om_lo);
   if (ctx->loc) cudaFree(ctx->loc);
   for (auto& kv : ctx->loc_scaled) cudaFree(kv.second);
+  for (auto& c : ctx->cosets) {
+    cudaFree(c.hi);
+    cudaFree(c.lo);
+  }
+  if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+  if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+  if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+  for (int i = 0; i < 3; ++i) {
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+  }
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   delete ctx;
 }
@@ -450,6 +558,66 @@ int ntt256_forward_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_
 }
 int ntt256_inverse_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch) {
   return transform_host(ctx, h_in, h_out, log_n, batch, true);
+}
+
+int ntt256_vec_mul(ntt256_ctx* ctx, void* d_out, const void* d_a, const void* d_b, unsigned long long n, int mont_form,
+                   ntt256_stream stream) {
+  if (!ctx || !d_out || !d_a || !d_b || (mont_form != 0 && mont_form != 1)) return NTT256_ERR_ARG;
+  if (n == 0) return NTT256_OK;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  Fe r2;
+  to_u32(ctx->hf.r2, r2.v);
+  const int threads = 128;
+  vec_mul_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      (uint4*)d_out, (const uint4*)d_a, (const uint4*)d_b, n, mont_form, ctx->fp, r2);
+  ++ctx->launches;
+  CTX_CUDA(cudaGetLastError());
+  return NTT256_OK;
+}
+
+static int vec_scale(ntt256_ctx* ctx, void* d_data, unsigned long long n, const U256& c_mont, cudaStream_t stream) {
+  if (!ctx || !d_data) return NTT256_ERR_ARG;
+  if (n == 0) return NTT256_OK;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  Fe c;
+  to_u32(c_mont, c.v);
+  const int threads = 128;
+  vec_scale_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>((uint4*)d_data, n, ctx->fp, c);
+  ++ctx->launches;
+  CTX_CUDA(cudaGetLastError());
+  return NTT256_OK;
+}
+
+int ntt256_to_montgomery(ntt256_ctx* ctx, void* d_data, unsigned long long n, ntt256_stream stream) {
+  if (!ctx) return NTT256_ERR_ARG;
+  return vec_scale(ctx, d_data, n, ctx->hf.r2, (cudaStream_t)stream);  // montmul(R^2, x) = x*R
+}
+int ntt256_from_montgomery(ntt256_ctx* ctx, void* d_data, unsigned long long n, ntt256_stream stream) {
+  if (!ctx) return NTT256_ERR_ARG;
+  return vec_scale(ctx, d_data, n, u256_small(1), (cudaStream_t)stream);  // montmul(1, x) = x/R
+}
+
+int ntt256_coset_forward(ntt256_ctx* ctx, void* d_data, int log_n, int batch, const uint32_t shift[8],
+                         ntt256_stream stream) {
+  if (!ctx || !d_data || !shift || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
+  U256 s = u256_from_limbs(shift);
+  if (u256_is_zero(s) || u256_cmp(s, ctx->hf.p) >= 0) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  int rc = coset_scale(ctx, d_data, log_n, batch, s, (cudaStream_t)stream);
+  if (rc) return rc;
+  return transform(ctx, d_data, log_n, batch, false, (cudaStream_t)stream);
+}
+
+int ntt256_coset_inverse(ntt256_ctx* ctx, void* d_data, int log_n, int batch, const uint32_t shift[8],
+                         ntt256_stream stream) {
+  if (!ctx || !d_data || !shift || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
+  U256 s = u256_from_limbs(shift);
+  if (u256_is_zero(s) || u256_cmp(s, ctx->hf.p) >= 0) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  int rc = transform(ctx, d_data, log_n, batch, true, (cudaStream_t)stream);
+  if (rc) return rc;
+  U256 sinv = ctx->hf.from_mont(ctx->hf.inv(ctx->hf.to_mont(s)));
+  return coset_scale(ctx, d_data, log_n, batch, sinv, (cudaStream_t)stream);
 }
 
 static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log_r, int log_p, int rank,

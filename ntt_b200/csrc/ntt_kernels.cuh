@@ -340,6 +340,55 @@ __global__ void twiddle_powers_kernel(uint4* __restrict__ out, const uint4* __re
   st_global_256(out + 2 * i, acc);
 }
 
+// ---------------------------------------------------------------- element-wise companions
+// (SURVEY.md par. 8f: the prover steps either side of an NTT -- pointwise product, Montgomery
+// form conversion, coset shift).  One thread per element, 256-bit loads/stores.
+//   mode 0: out = a*b      canonical in/out          (two products: (a*b/R) * R^2/R)
+//   mode 1: out = a*b/R    Montgomery-form in/out    (one product)
+__global__ void vec_mul_kernel(uint4* __restrict__ out, const uint4* __restrict__ a, const uint4* __restrict__ b,
+                               unsigned long long n, int mode, const __grid_constant__ FieldParams f,
+                               const __grid_constant__ Fe r2) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 x[8], y[8];
+  ld_global_256(x, a + 2 * i);
+  ld_global_256(y, b + 2 * i);
+  mul_by(y, x, f);  // x canonical (< p) is a valid left operand
+  if (mode == 0) mul_by(y, r2.v, f);
+  canonicalize(y, f);
+  st_global_256(out + 2 * i, y);
+}
+
+// x <- c * x for a Montgomery-form constant c (R^2: to Montgomery form; 1: from Montgomery form)
+__global__ void vec_scale_kernel(uint4* __restrict__ data, unsigned long long n, const __grid_constant__ FieldParams f,
+                                 const __grid_constant__ Fe c) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 x[8];
+  ld_global_256(x, data + 2 * i);
+  mul_by(x, c.v, f);
+  canonicalize(x, f);
+  st_global_256(data + 2 * i, x);
+}
+
+// x[j] <- s^j * x[j] with s^j = hi[j >> lo_bits] * lo[j & mask] (both tables in Montgomery form);
+// j is the index inside one transform of 2^log_n points (batched arrays repeat the pattern).
+__global__ void coset_scale_kernel(uint4* __restrict__ data, unsigned long long n, int log_n, int lo_bits,
+                                   const uint4* __restrict__ hi, const uint4* __restrict__ lo,
+                                   const __grid_constant__ FieldParams f) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32 j = (u32)(i & ((1ull << log_n) - 1ull));
+  u32 x[8], w[8];
+  ld_global_256(x, data + 2 * i);
+  ld_table(w, hi, j >> lo_bits);
+  mul_by(x, w, f);
+  ld_table(w, lo, j & ((1u << lo_bits) - 1u));
+  mul_by(x, w, f);
+  canonicalize(x, f);
+  st_global_256(data + 2 * i, x);
+}
+
 // out[i] = c * in[i]  (c Montgomery-form constant): scaled copies of small tables.
 __global__ void table_scale_kernel(uint4* __restrict__ out, const uint4* __restrict__ in, unsigned long long count,
                                    const __grid_constant__ FieldParams f, const __grid_constant__ Fe c) {

@@ -19,6 +19,8 @@ EXPORTS = [
     "ntt256_forward", "ntt256_inverse", "ntt256_forward_batch", "ntt256_inverse_batch",
     "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2", "ntt256_fourstep_step1_peer", "ntt256_enable_peer_access",
     "ntt256_ipc_alloc", "ntt256_ipc_open", "ntt256_ipc_close", "ntt256_ipc_free",
+    "ntt256_vec_mul", "ntt256_to_montgomery", "ntt256_from_montgomery", "ntt256_coset_forward",
+    "ntt256_coset_inverse",
     "ntt256_plan_describe", "ntt256_plan_describe_fourstep", "ntt256_launch_count", "ntt256_strerror", "ntt256_last_cuda_error",
     "ntt256_version",
 ]
@@ -55,6 +57,11 @@ def lib() -> ctypes.CDLL:
         for name in ("ntt256_fourstep_step1", "ntt256_fourstep_step2"):
             getattr(L, name).argtypes = [vp, vp, ci, ci, ci, ci, vp]
         L.ntt256_fourstep_step1_peer.argtypes = [vp, vp, ctypes.POINTER(vp), ci, ci, ci, ci, vp]
+        L.ntt256_vec_mul.argtypes = [vp, vp, vp, vp, ctypes.c_ulonglong, ci, vp]
+        for name in ("ntt256_to_montgomery", "ntt256_from_montgomery"):
+            getattr(L, name).argtypes = [vp, vp, ctypes.c_ulonglong, vp]
+        for name in ("ntt256_coset_forward", "ntt256_coset_inverse"):
+            getattr(L, name).argtypes = [vp, vp, ci, ci, u32p, vp]
         L.ntt256_enable_peer_access.argtypes = [ci, ci]
         L.ntt256_ipc_alloc.argtypes = [ci, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
         L.ntt256_ipc_open.argtypes = [ci, ctypes.c_char_p, ctypes.POINTER(vp)]

@@ -399,3 +399,87 @@ def test_montgomery_form_data_is_transparent(torch_cuda, ctxs):
     got = co.array_to_ints(_gpu_forward(torch_cuda, ctx, xm, log_n))
     want = co.array_to_ints(co.ntt(co.ints_to_array(vals), p, g, threads=4))
     assert got == [v * R % p for v in want]
+
+
+# --------------------------------------------------------------------------- SURVEY par. 8f rows
+def test_vec_mul_and_montgomery_conversions(torch_cuda, ctxs):
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    for field in ("bn254_fr", "bls12_381_fr"):
+        p, g = FIELDS[field]
+        R = (1 << 256) % p
+        Rinv = pow(R, -1, p)
+        ctx = ctxs(field, 20)
+        n = 5000  # not a multiple of the block size
+        a = co.array_to_ints(co.splitmix_elements(n, p, 1)) 
+        b = co.array_to_ints(co.splitmix_elements(n, p, 2))
+        a[0], b[0], a[1], b[1], a[2], b[2] = p - 1, p - 1, 0, 5, 1, p - 1
+        da = torch.from_numpy(co.ints_to_array(a).view(np.int32)).cuda().view(-1)
+        db = torch.from_numpy(co.ints_to_array(b).view(np.int32)).cuda().view(-1)
+        out = torch.empty_like(da)
+        ctx.vec_mul(da, db, out=out)
+        torch.cuda.synchronize()
+        assert co.array_to_ints(out.cpu().numpy().view(np.uint32).reshape(-1, 8)) == [x * y % p for x, y in zip(a, b)]
+        ctx.vec_mul(da, db, out=out, mont_form=True)
+        torch.cuda.synchronize()
+        assert co.array_to_ints(out.cpu().numpy().view(np.uint32).reshape(-1, 8)) == [x * y * Rinv % p for x, y in zip(a, b)]
+        m = da.clone()
+        ctx.to_montgomery(m)
+        torch.cuda.synchronize()
+        assert co.array_to_ints(m.cpu().numpy().view(np.uint32).reshape(-1, 8)) == [x * R % p for x in a]
+        ctx.from_montgomery(m)
+        torch.cuda.synchronize()
+        assert torch.equal(m, da)
+        # in-place product (out aliases a)
+        ctx.vec_mul(m, db)
+        torch.cuda.synchronize()
+        assert co.array_to_ints(m.cpu().numpy().view(np.uint32).reshape(-1, 8)) == [x * y % p for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize("log_n,batch", [(0, 1), (2, 3), (9, 1), (13, 2), (16, 1)])
+def test_coset_transforms(torch_cuda, ctxs, log_n, batch):
+    """X[k] = sum_j shift^j x[j] w^(jk): oracle = the reference NTT of the pre-scaled input."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 20)
+    n = 1 << log_n
+    for shift in (g, 0x1234567890ABCDEF1234567890ABCDEF % p):
+        x = co.splitmix_elements(n * batch, p, 1000 + log_n)
+        xi = co.array_to_ints(x)
+        pw = [1] * n
+        for j in range(1, n):
+            pw[j] = pw[j - 1] * shift % p
+        scaled = co.ints_to_array([xi[b * n + j] * pw[j] % p for b in range(batch) for j in range(n)])
+        want = np.concatenate([co.ntt(scaled[b * n:(b + 1) * n], p, g, threads=4) for b in range(batch)])
+        d = torch.from_numpy(x.view(np.int32)).cuda().view(-1)
+        ctx.coset_forward(d, log_n, shift, batch=batch)
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 8), want)
+        ctx.coset_inverse(d, log_n, shift, batch=batch)
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 8), x)
+
+
+def test_pipelined_host_batches(torch_cuda, ctxs):
+    """Host-buffer entry point with a batch large enough to be streamed in chunks (3-slot ring,
+    uplink / kernels / downlink on separate streams): same bits as transform-by-transform."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 20)
+    log_n, batch = 12, 1100  # 128 KiB per transform -> chunks of 256 transforms, last one partial
+    x = co.splitmix_elements(batch << log_n, p, 31337)
+    h_in = torch.from_numpy(x.view(np.int32)).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    got = ctx.forward_host(h_in.numpy().view(np.uint32), log_n, batch=batch, out=h_out.numpy().view(np.uint32)).reshape(-1, 8)
+    for b in list(range(0, batch, 97)) + [255, 256, 767, 768, 1023, 1024, batch - 1]:
+        assert np.array_equal(got[b << log_n:(b + 1) << log_n], co.ntt(x[b << log_n:(b + 1) << log_n], p, g)), b
+    back = ctx.inverse_host(got, log_n, batch=batch).reshape(-1, 8)   # pageable memory path
+    assert np.array_equal(back, x)
