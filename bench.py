@@ -118,7 +118,7 @@ def cpu_baseline(sample_log_n: int, threads: int, reps: int = 1):
 def run_reference(args):
     """--impl reference: the reference's CPU path.  The reference has no 256-bit CPU NTT (its
     NTT() is int64 over a 29-bit prime), so this arm times the oracle port -- the same algorithm
-    over BN254 Fr -- with every host thread, on a bounded sample (2^20 points per step), and also
+    over BN254 Fr -- with every host thread, on a bounded sample (2^22 points per step), and also
     reports the literal reference NTT() (oracle/_ref, int64) for continuity."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -126,7 +126,7 @@ def run_reference(args):
     from oracle import c_oracle
 
     threads = max(1, os.cpu_count() or 1)
-    sample_log_n = 20
+    sample_log_n = 22
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(sample_log_n, threads)
     t_total = 0.0
@@ -333,11 +333,11 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = max(1, os.cpu_count() or 1)
-        v, secs = cpu_baseline(20, threads)
-        v1, secs1 = cpu_baseline(18, 1)
+        v, secs = cpu_baseline(23, threads)
+        v1, secs1 = cpu_baseline(19, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"2^20-point forward NTT of the same field, {secs:.2f} s; "
-                                          f"single thread (reference convention) 2^18 points: {v1:.0f} elements/s"}
+                                "sample": f"2^23-point forward NTT of the same field on {threads} threads, {secs:.2f} s wall; "
+                                          f"single thread (the reference's convention) 2^19 points: {v1:.0f} elements/s"}
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()

@@ -6,7 +6,9 @@
 //  core_add_sub.cu:27-49) with single-thread carry chains:
 //   * Montgomery product on mad.lo.cc / madc.hi.cc chains laid out "even/odd"
 //     so that ptxas fuses every lo/hi pair into one IMAD.WIDE.U32(.X) -- 128 wide
-//     multiply-accumulates + 8 low multiplies per product, zero shuffles;
+//     multiply-accumulates + 8 low multiplies per product, zero shuffles (measured on
+//     B200: 66 G products/s; the carry-predicate forms issue at half the plain IMAD.WIDE
+//     rate, see profiles/r01_microbench_notes.md);
 //   * data stay canonical (non-Montgomery) in memory, twiddles are kept in
 //     Montgomery form, so  montmul(w*R, x) = w*x mod p  needs no bn2mont/mont2bn
 //     (the reference converts 2+1 times per butterfly, big-num.cu:88-92);

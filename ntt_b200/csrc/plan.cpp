@@ -9,8 +9,7 @@
 namespace ntt256 {
 namespace {
 
-constexpr int kFreq = 64;
-constexpr int kPassenger = 128;
+constexpr int kFreq = 64;  // labels: [0,64) time bit j_b, [64,128) frequency bit k_c, >= 128 passenger
 
 struct Ctx {
   int nbits;       // local physical index bits
@@ -122,9 +121,8 @@ struct Search {
       int l = lab_after(p);
       int fl = final_label(c, l, time_hi_all, c.time_lo);
       int dp = c.dest_of_label[fl];
-      bool settled_kind = (l == fl);  // already in final form
-      if (dp >= 0 && in[dp] && (settled_kind || true)) {
-        // labels still to be processed may also wait at their destination
+      if (dp >= 0 && in[dp]) {
+        // (labels still to be processed may also wait at their destination)
         slot_label[dp] = l;
       } else {
         leftovers.push_back(p);
