@@ -211,11 +211,23 @@ NTT_DEV void add_lazy(u32* s, const u32* a, const u32* b, const FieldParams& f) 
   for (int k = 0; k < 8; ++k) s[k] = (t[k] & keep_t) | (d[k] & ~keep_t);
 }
 
-// d = a - b  (mod 2p window): add 2p back on borrow.
+// d = a - b  (mod 2p window): add 2p back on borrow.  The add-back is a predicated carry chain
+// (8 instructions) instead of mask-then-add (16): all integer instructions share one issue port.
 NTT_DEV void sub_lazy(u32* d, const u32* a, const u32* b, const FieldParams& f) {
-  u32 t[8];
-  u32 bw = sub256(t, a, b);
-  add256_masked(d, t, f.p2, bw);
+  u32 bw = sub256(d, a, b);
+  asm("{\n\t.reg .pred q;\n\t"
+      "setp.ne.u32 q, %8, 0;\n\t"
+      "@q add.cc.u32   %0, %0, %9;\n\t"
+      "@q addc.cc.u32  %1, %1, %10;\n\t"
+      "@q addc.cc.u32  %2, %2, %11;\n\t"
+      "@q addc.cc.u32  %3, %3, %12;\n\t"
+      "@q addc.cc.u32  %4, %4, %13;\n\t"
+      "@q addc.cc.u32  %5, %5, %14;\n\t"
+      "@q addc.cc.u32  %6, %6, %15;\n\t"
+      "@q addc.u32     %7, %7, %16;\n\t}"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7])
+      : "r"(bw), "r"(f.p2[0]), "r"(f.p2[1]), "r"(f.p2[2]), "r"(f.p2[3]), "r"(f.p2[4]), "r"(f.p2[5]), "r"(f.p2[6]),
+        "r"(f.p2[7]));
 }
 
 // [0,2p) -> [0,p)
