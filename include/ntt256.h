@@ -65,6 +65,13 @@ void ntt256_ctx_destroy(ntt256_ctx* ctx);
  * plans are discarded. */
 int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits);
 
+/* The first pass of a transform longer than 2^18 points needs twiddles w_n^e with a 2^log_n-wide
+ * exponent range: either two table lookups and one extra product per element, or one coalesced
+ * read from an n-entry array laid out like the pass's output (32*n bytes per (size, direction),
+ * built on first use, kept in the context).  Arrays up to max_bytes are built automatically
+ * (default 1 GiB, i.e. n <= 2^25); 0 selects the two-lookup path always. */
+int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes);
+
 /* Forward NTT of 2^log_n points, in place on device memory, natural order in and out.
  * == NTT_GZKP<8,256>(data, 1<<log_n, ..., prime, omega, B, G)  (big-num.cu:458). */
 int ntt256_forward(ntt256_ctx* ctx, void* d_data, int log_n, ntt256_stream stream);

@@ -100,6 +100,10 @@ class Ntt256:
     def set_tuning(self, tile_bits: int, coalesce_bits: int):
         self._check(self._L.ntt256_ctx_set_tuning(self._h, tile_bits, coalesce_bits))
 
+    def set_stream_twiddle_limit(self, max_bytes: int):
+        """Largest streamed first-pass twiddle array built automatically (0: always two lookups)."""
+        self._check(self._L.ntt256_ctx_set_stream_twiddle_limit(self._h, max_bytes))
+
     @property
     def launch_count(self) -> int:
         return int(self._L.ntt256_launch_count(self._h))

@@ -54,6 +54,10 @@ struct ntt256_ctx {
   int coalesce_bits = 2;
   bool auto_tile = true;                  // shrink the tile for small problems so the grid fills the chip
   std::map<int, uint4*> loc_scaled;       // log_n -> (1/n) * loc[] : folds the inverse scaling into a round twiddle
+  // streamed pass-twiddle arrays, keyed by (plan id, pass index, direction)
+  std::map<std::tuple<unsigned long long, int, int>, uint4*> tw_streams;
+  size_t tw_stream_limit = (size_t)1 << 30;   // largest array built automatically (bytes); 0 = never
+  unsigned long long next_plan_id = 1;
   struct CosetTables {
     U256 shift;
     int log_n, lo_bits;
@@ -174,6 +178,7 @@ int get_plan(ntt256_ctx* ctx, const PlanKey& key, const Plan** out) {
         build_request(key, key.tile_bits ? key.tile_bits : ctx->tile_bits, ctx->coalesce_bits, ctx->max_log_n);
     Plan plan;
     if (!make_plan(req, &plan)) return NTT256_ERR_PLAN;
+    plan.id = ctx->next_plan_id++;
     it = ctx->plans.emplace(key, plan).first;
   }
   *out = &it->second;
@@ -233,6 +238,34 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
         A.loc_scaled = loc_scaled;
       } else {
         A.pd.scale_out = 1;
+      }
+    }
+    // streamed twiddles for a pass that would otherwise need the two-factor product
+    A.tw_stream = nullptr;
+    A.tw_gen_out = nullptr;
+    if (A.pd.has_tw && A.pd.tw_lshift < ctx->lo_bits && ctx->tw_stream_limit > 0) {
+      const size_t tbytes = (size_t)32 << (A.pd.T + A.pd.nblk_bits);
+      if (tbytes <= ctx->tw_stream_limit) {
+        auto tkey = std::make_tuple(plan.id, (int)i, inverse ? 1 : 0);
+        auto ts = ctx->tw_streams.find(tkey);
+        if (ts == ctx->tw_streams.end()) {
+          uint4* tab = nullptr;
+          if (cudaMalloc((void**)&tab, tbytes) == cudaSuccess) {
+            PassArgs G = A;
+            G.tw_gen_out = tab;
+            G.peer_bits = 0;
+            to_u32(ctx->hf.one, G.one);
+            const int Tg = G.pd.T;
+            dim3 ggrid((unsigned)(1ull << G.pd.nblk_bits), 1, 1);
+            ntt_pass_kernel<<<ggrid, 1u << (Tg - 3), (size_t)32 << Tg, stream>>>((uint4*)d_data, G);
+            ++ctx->launches;
+            CTX_CUDA(cudaGetLastError());
+            ts = ctx->tw_streams.emplace(tkey, tab).first;
+          } else {
+            cudaGetLastError();  // not enough memory: keep the two-lookup path
+          }
+        }
+        if (ts != ctx->tw_streams.end()) A.tw_stream = ts->second;
       }
     }
     if (peer && i + 1 == plan.passes.size()) {
@@ -514,6 +547,7 @@ void ntt256_ctx_destroy(ntt256_ctx* ctx) {
   if (ctx->om_lo) cudaFree(ctx->om_lo);
   if (ctx->loc) cudaFree(ctx->loc);
   for (auto& kv : ctx->loc_scaled) cudaFree(kv.second);
+  for (auto& kv : ctx->tw_streams) cudaFree(kv.second);
   for (auto& c : ctx->cosets) {
     cudaFree(c.hi);
     cudaFree(c.lo);
@@ -538,6 +572,8 @@ int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits) {
   ctx->coalesce_bits = coalesce_bits;
   ctx->auto_tile = false;
   ctx->plans.clear();
+  for (auto& kv : ctx->tw_streams) cudaFree(kv.second);
+  ctx->tw_streams.clear();
   return NTT256_OK;
 }
 
@@ -688,6 +724,16 @@ int ntt256_ipc_close(int device, void* d_ptr) {
 int ntt256_ipc_free(int device, void* d_ptr) {
   if (cudaSetDevice(device) != cudaSuccess) return NTT256_ERR_CUDA;
   return cudaFree(d_ptr) == cudaSuccess ? NTT256_OK : NTT256_ERR_CUDA;
+}
+
+int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes) {
+  if (!ctx) return NTT256_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->tw_stream_limit = max_bytes;
+  for (auto& kv : ctx->tw_streams) cudaFree(kv.second);
+  ctx->tw_streams.clear();
+  return NTT256_OK;
 }
 
 int ntt256_enable_peer_access(int device, int peer_device) {

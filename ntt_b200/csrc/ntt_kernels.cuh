@@ -43,6 +43,14 @@ struct PassArgs {
   // and multiplies all 8 elements (also the one whose twiddle is 1), which applies the 1/n.
   int scaled_round;
   const uint4* loc_scaled;
+  // Streamed pass twiddles.  A pass whose twiddle exponent does not fit one table lookup (the first
+  // pass of a transform longer than 2^hi_bits) would need two lookups and an extra product per
+  // element; instead its n twiddles can be kept in an array laid out exactly like the pass's
+  // output (read with the same coalesced 256-bit accesses as the stores): HBM has ~6x headroom
+  // on this path, the integer pipe none.  tw_gen_out != null: the launch only WRITES that array.
+  const uint4* tw_stream;
+  uint4* tw_gen_out;
+  u32 one[8];  // R mod p
 };
 
 // ---------------------------------------------------------------- element I/O
@@ -112,15 +120,17 @@ ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
 
   // ---- block-level index pieces (uniform)
   const unsigned long long blk = blockIdx.x;
-  unsigned long long base = deposit64(blk, pd.blk_pos, pd.nblk_bits);
+  const unsigned long long base_t = deposit64(blk, pd.blk_pos, pd.nblk_bits);  // index inside one transform
+  unsigned long long base = base_t;
   u32 jlow_blk = pd.jlow_const;
   for (int i = 0; i < pd.nblk_bits; ++i) jlow_blk += (u32)((blk >> i) & 1ull) * pd.wt_blk[i];
   base += (unsigned long long)blockIdx.y * A.batch_stride;
   uint4* gbase = data + 2 * base;
 
   u32 x[8][8];
+  const bool gen = (A.tw_gen_out != nullptr);
 
-  for (int r = 0; r < pd.nrounds; ++r) {
+  for (int r = gen ? pd.nrounds - 1 : 0; r < pd.nrounds; ++r) {
     const int sb = pd.round_sb[r];
     const int nb = pd.round_nb[r];
     const u32 lam0 = deposit32(tid, pd.tmap[r], T - 3);
@@ -128,7 +138,12 @@ ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
     const bool last = (r == pd.nrounds - 1);
 
     // ---- fetch the 8 elements of this thread
-    if (first) {
+    if (gen) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[u][k] = A.one[k];
+    } else if (first) {
       const u32 g0 = deposit32(lam0, pd.in_pos, T);
       const u32 s0 = 1u << pd.in_pos[sb], s1 = 1u << pd.in_pos[sb + 1], s2 = 1u << pd.in_pos[sb + 2];
 #pragma unroll
@@ -147,7 +162,8 @@ ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
     }
 
     // ---- butterflies on the top nb bits of the 3-bit group
-    if (nb == 3) {
+    if (gen) {
+    } else if (nb == 3) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         bfly(x[u], x[u + 4], f);
@@ -217,7 +233,17 @@ ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
     } else {
       // ---- pass twiddle, scale, canonical form, store
       const int lowp = T - d;
-      if (pd.has_tw) {
+      const u32 g0 = deposit32(lam0, pd.out_pos, T);
+      const u32 s0 = 1u << pd.out_pos[sb], s1 = 1u << pd.out_pos[sb + 1], s2 = 1u << pd.out_pos[sb + 2];
+      if (pd.has_tw && A.tw_stream != nullptr && !gen) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const u32 off = (u32)base_t + g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+          u32 w[8];
+          ld_table(w, A.tw_stream, off);
+          mul_by(x[u], w, f);
+        }
+      } else if (pd.has_tw) {
         u32 jl0 = jlow_blk;
         for (int i = 0; i < lowp; ++i) jl0 += ((lam0 >> i) & 1u) * pd.wt_loc[i];
         const u32 gw0 = (sb + 0 < lowp) ? pd.wt_loc[sb + 0] : 0u;
@@ -254,9 +280,14 @@ ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
       // a single-round pass loads and stores global memory in the same round: every thread of
       // the CTA must have loaded before any permuted store lands on another thread's input
       if (first) __syncthreads();
-      const u32 g0 = deposit32(lam0, pd.out_pos, T);
-      const u32 s0 = 1u << pd.out_pos[sb], s1 = 1u << pd.out_pos[sb + 1], s2 = 1u << pd.out_pos[sb + 2];
-      if (A.peer_bits == 0) {
+      if (gen) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const u32 off = (u32)base_t + g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+          canonicalize(x[u], f);
+          st_global_256(A.tw_gen_out + 2 * (size_t)off, x[u]);
+        }
+      } else if (A.peer_bits == 0) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const u32 off = g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);

@@ -52,6 +52,7 @@ struct Plan {
   int tile_bits = 0;   // requested T
   int coalesce_bits = 0;
   std::vector<PassDesc> passes;
+  unsigned long long id = 0;     // unique per created plan (keys per-plan device tables)
   std::string describe() const;  // JSON, for tests and DESIGN.md
 };
 

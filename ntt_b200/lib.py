@@ -16,6 +16,7 @@ FIELD_BN254_FR, FIELD_BLS12_381_FR = 0, 1
 # every symbol include/ntt256.h declares
 EXPORTS = [
     "ntt256_ctx_create", "ntt256_ctx_create_named", "ntt256_ctx_destroy", "ntt256_ctx_set_tuning",
+    "ntt256_ctx_set_stream_twiddle_limit",
     "ntt256_forward", "ntt256_inverse", "ntt256_forward_batch", "ntt256_inverse_batch",
     "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2", "ntt256_fourstep_step1_peer", "ntt256_enable_peer_access",
     "ntt256_ipc_alloc", "ntt256_ipc_open", "ntt256_ipc_close", "ntt256_ipc_free",
@@ -48,6 +49,7 @@ def lib() -> ctypes.CDLL:
         L.ntt256_ctx_destroy.argtypes = [vp]
         L.ntt256_ctx_destroy.restype = None
         L.ntt256_ctx_set_tuning.argtypes = [vp, ci, ci]
+        L.ntt256_ctx_set_stream_twiddle_limit.argtypes = [vp, ctypes.c_size_t]
         for name in ("ntt256_forward", "ntt256_inverse"):
             getattr(L, name).argtypes = [vp, vp, ci, vp]
         for name in ("ntt256_forward_batch", "ntt256_inverse_batch"):

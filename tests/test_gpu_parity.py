@@ -483,3 +483,22 @@ def test_pipelined_host_batches(torch_cuda, ctxs):
         assert np.array_equal(got[b << log_n:(b + 1) << log_n], co.ntt(x[b << log_n:(b + 1) << log_n], p, g)), b
     back = ctx.inverse_host(got, log_n, batch=batch).reshape(-1, 8)   # pageable memory path
     assert np.array_equal(back, x)
+
+
+def test_streamed_and_two_lookup_twiddles_agree(torch_cuda):
+    """The first pass of a transform longer than 2^18 takes its twiddles either from a streamed
+    n-entry array (default) or from two table lookups and an extra product (limit 0): same bits,
+    forward and inverse, also after switching back and forth."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    p, g = FIELDS["bls12_381_fr"]
+    ctx = Ntt256("bls12_381_fr", max_log_n=22)
+    x = co.splitmix_elements(1 << 21, p, 2121)
+    want = co.ntt(x, p, g, threads=8)
+    for limit in (0, 1 << 30, 0, 1 << 26):
+        ctx.set_stream_twiddle_limit(limit)
+        got = _gpu_forward(torch_cuda, ctx, x, 21)
+        assert np.array_equal(got, want), limit
+        assert np.array_equal(_gpu_forward(torch_cuda, ctx, got, 21, inverse=True), x), limit
+    ctx.close()
