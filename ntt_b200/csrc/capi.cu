@@ -53,6 +53,7 @@ struct ntt256_ctx {
   int tile_bits = 11;
   int coalesce_bits = 2;
   bool auto_tile = true;                  // shrink the tile for small problems so the grid fills the chip
+  bool zero_copy_host = true;             // *_host entry points: first/last pass access pinned host memory directly
   std::map<int, uint4*> loc_scaled;       // log_n -> (1/n) * loc[] : folds the inverse scaling into a round twiddle
   // streamed pass-twiddle arrays, keyed by (plan id, pass index, direction)
   std::map<std::tuple<unsigned long long, int, int>, uint4*> tw_streams;
@@ -189,9 +190,13 @@ struct PeerSpec {
   const void* const* ptrs = nullptr;
   int bits = 0, shift = 0, rank = 0;
 };
+struct IoSpec {  // optional out-of-place ends of a plan (device-visible pointers)
+  const void* src_first = nullptr;
+  void* dst_last = nullptr;
+};
 
 int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long batch_stride, int batch, bool inverse,
-             int scale_log_n, cudaStream_t stream, const PeerSpec* peer = nullptr) {
+             int scale_log_n, cudaStream_t stream, const PeerSpec* peer = nullptr, const IoSpec* io = nullptr) {
   PassArgs A;
   std::memset(&A, 0, sizeof(A));
   A.f = ctx->fp;
@@ -257,7 +262,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
             to_u32(ctx->hf.one, G.one);
             const int Tg = G.pd.T;
             dim3 ggrid((unsigned)(1ull << G.pd.nblk_bits), 1, 1);
-            ntt_pass_kernel<<<ggrid, 1u << (Tg - 3), (size_t)32 << Tg, stream>>>((uint4*)d_data, G);
+            ntt_pass_kernel<<<ggrid, 1u << (Tg - 3), (size_t)32 << Tg, stream>>>((const uint4*)d_data, (uint4*)d_data, G);
             ++ctx->launches;
             CTX_CUDA(cudaGetLastError());
             ts = ctx->tw_streams.emplace(tkey, tab).first;
@@ -280,7 +285,10 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
     const unsigned long long nblk = 1ull << A.pd.nblk_bits;
     if (nblk > 0x7fffffffull || batch > 65535) return NTT256_ERR_ARG;
     dim3 grid((unsigned)nblk, (unsigned)batch, 1);
-    ntt_pass_kernel<<<grid, threads, smem, stream>>>((uint4*)d_data, A);
+    // first pass may read from `src_first`, last pass may write to `dst_last` (host-mapped buffers)
+    const uint4* pin = (i == 0 && io && io->src_first) ? (const uint4*)io->src_first : (const uint4*)d_data;
+    uint4* pout = (i + 1 == plan.passes.size() && io && io->dst_last) ? (uint4*)io->dst_last : (uint4*)d_data;
+    ntt_pass_kernel<<<grid, threads, smem, stream>>>(pin, pout, A);
     ++ctx->launches;
     CTX_CUDA(cudaGetLastError());
   }
@@ -307,7 +315,8 @@ int run_tiny(ntt256_ctx* ctx, void* d_data, int log_n, unsigned long long batch,
   return NTT256_OK;
 }
 
-int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse, cudaStream_t stream) {
+int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse, cudaStream_t stream,
+              const IoSpec* io = nullptr) {
   if (!ctx || !d_data || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
   CTX_CUDA(cudaSetDevice(ctx->device));
   if (log_n < 3) return run_tiny(ctx, d_data, log_n, (unsigned long long)batch, inverse, stream);
@@ -331,7 +340,8 @@ int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse,
   for (int b0 = 0; b0 < batch; b0 += kSlice) {
     const int nb = std::min(kSlice, batch - b0);
     char* p = (char*)d_data + ((size_t)b0 << log_n) * 32;
-    rc = run_plan(ctx, *plan, p, 1ull << log_n, nb, inverse, inverse ? log_n : -1, stream);
+    rc = run_plan(ctx, *plan, p, 1ull << log_n, nb, inverse, inverse ? log_n : -1, stream, nullptr,
+                  (io && batch <= kSlice) ? io : nullptr);
     if (rc) return rc;
   }
   return NTT256_OK;
@@ -362,6 +372,26 @@ int transform_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, in
   if (batch < 2 * per_chunk || batch < 4) {
     int rc = ensure_stage(ctx, bytes);
     if (rc) return rc;
+    // Pinned (mapped) host buffers: the first pass loads straight from host memory and the last
+    // pass stores straight to it, so the PCIe transfers overlap those passes.
+    if (log_n >= 3 && ctx->zero_copy_host) {
+      cudaPointerAttributes ai, ao;
+      void *din = nullptr, *dout = nullptr;
+      bool ok = cudaPointerGetAttributes(&ai, h_in) == cudaSuccess && ai.type == cudaMemoryTypeHost &&
+                cudaPointerGetAttributes(&ao, h_out) == cudaSuccess && ao.type == cudaMemoryTypeHost &&
+                cudaHostGetDevicePointer(&din, (void*)h_in, 0) == cudaSuccess &&
+                cudaHostGetDevicePointer(&dout, h_out, 0) == cudaSuccess;
+      cudaGetLastError();
+      if (ok) {
+        IoSpec io;
+        io.src_first = din;
+        io.dst_last = dout;
+        rc = transform(ctx, ctx->d_stage, log_n, batch, inverse, 0, &io);
+        if (rc) return rc;
+        CTX_CUDA(cudaStreamSynchronize(0));
+        return NTT256_OK;
+      }
+    }
     CTX_CUDA(cudaMemcpyAsync(ctx->d_stage, h_in, bytes, cudaMemcpyHostToDevice, 0));
     rc = transform(ctx, ctx->d_stage, log_n, batch, inverse, 0);
     if (rc) return rc;

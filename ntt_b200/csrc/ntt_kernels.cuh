@@ -109,7 +109,10 @@ NTT_DEV unsigned long long deposit64(unsigned long long v, const int8_t* pos, in
 }
 
 __global__ void __launch_bounds__(512, 1)
-ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
+ntt_pass_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
+  // data_in == data_out: in place (the normal case).  They differ when the first / last pass of
+  // a host-buffer transform reads / writes pinned host memory directly (zero-copy over PCIe, so the
+  // transfer overlaps the pass instead of preceding / following it).
   extern __shared__ u32 smem[];
   const PassDesc& pd = A.pd;
   const FieldParams& f = A.f;
@@ -125,7 +128,8 @@ ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
   u32 jlow_blk = pd.jlow_const;
   for (int i = 0; i < pd.nblk_bits; ++i) jlow_blk += (u32)((blk >> i) & 1ull) * pd.wt_blk[i];
   base += (unsigned long long)blockIdx.y * A.batch_stride;
-  uint4* gbase = data + 2 * base;
+  const uint4* gbase_in = data_in + 2 * base;
+  uint4* gbase = data_out + 2 * base;
 
   u32 x[8][8];
   const bool gen = (A.tw_gen_out != nullptr);
@@ -149,7 +153,7 @@ ntt_pass_kernel(uint4* __restrict__ data, const __grid_constant__ PassArgs A) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const u32 off = g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
-        ld_global_256(x[u], gbase + 2 * (size_t)off);
+        ld_global_256(x[u], gbase_in + 2 * (size_t)off);
       }
     } else {
       const u32 w0 = swz(lam0);

@@ -502,3 +502,29 @@ def test_streamed_and_two_lookup_twiddles_agree(torch_cuda):
         assert np.array_equal(got, want), limit
         assert np.array_equal(_gpu_forward(torch_cuda, ctx, got, 21, inverse=True), x), limit
     ctx.close()
+
+
+def test_zero_copy_host_buffers(torch_cuda, ctxs):
+    """Pinned host buffers: the first pass reads host memory and the last pass writes it directly
+    (no staging copies).  Distinct and aliased in/out buffers, one pass and several passes."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 24)
+    for log_n, batch in ((5, 1), (10, 3), (14, 1), (20, 1), (21, 2)):
+        x = co.splitmix_elements(batch << log_n, p, 4000 + log_n)
+        h_in = torch.from_numpy(x.view(np.int32).copy()).pin_memory()
+        h_out = torch.zeros_like(h_in).pin_memory()
+        got = ctx.forward_host(h_in.numpy().view(np.uint32), log_n, batch=batch, out=h_out.numpy().view(np.uint32)).reshape(-1, 8)
+        assert np.array_equal(h_in.numpy().view(np.uint32).reshape(-1, 8), x), "input buffer must be untouched"
+        n = 1 << log_n
+        for b in range(batch):
+            assert np.array_equal(got[b * n:(b + 1) * n], co.ntt(x[b * n:(b + 1) * n], p, g, threads=8)), (log_n, b)
+        # aliased: transform the pinned buffer in place, then invert it in place
+        buf = h_in.numpy().view(np.uint32)
+        ctx.forward_host(buf, log_n, batch=batch, out=buf)
+        assert np.array_equal(buf.reshape(-1, 8), got)
+        ctx.inverse_host(buf, log_n, batch=batch, out=buf)
+        assert np.array_equal(buf.reshape(-1, 8), x)
