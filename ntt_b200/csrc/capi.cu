@@ -22,7 +22,8 @@ using namespace ntt256;
 
 namespace {
 
-constexpr int kHiBitsMax = 18;  // w^(i<<lo) table: 2^18 entries = 8 MiB, stays in L2
+constexpr int kHiBitsMax = 18;       // w^(i<<lo) table: 2^18 entries = 8 MiB, stays in L2
+constexpr int kHiBitsMaxLarge = 20;  // contexts for >= 2^26 points: 32 MiB, one two-factor pass less (2^28: -6 %)
 constexpr int kLocBitsMax = 12;
 
 struct PlanKey {
@@ -510,7 +511,7 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
       return NTT256_ERR_FIELD;
     }
   }
-  ctx->hi_bits = std::min(max_log_n, kHiBitsMax);
+  ctx->hi_bits = std::min(max_log_n, max_log_n >= 26 ? kHiBitsMaxLarge : kHiBitsMax);
   ctx->lo_bits = max_log_n - ctx->hi_bits;
   ctx->loc_bits = std::min(max_log_n, kLocBitsMax);
   std::memset(ctx->c8, 0, sizeof(ctx->c8));
