@@ -179,7 +179,18 @@ int get_plan(ntt256_ctx* ctx, const PlanKey& key, const Plan** out) {
     PlanRequest req =
         build_request(key, key.tile_bits ? key.tile_bits : ctx->tile_bits, ctx->coalesce_bits, ctx->max_log_n);
     Plan plan;
-    if (!make_plan(req, &plan)) return NTT256_ERR_PLAN;
+    bool ok = make_plan(req, &plan);
+    // very small tiles with wide coalescing leave too few free tile bits: relax the run length
+    // first, then allow more passes, then grow the tile
+    for (int g = req.coalesce_bits - 1; !ok && g >= 0; --g) {
+      req.coalesce_bits = g;
+      ok = make_plan(req, &plan, 12);
+    }
+    for (int t = req.tile_bits + 1; !ok && t <= kMaxTileBits; ++t) {
+      req.tile_bits = t;
+      ok = make_plan(req, &plan, 12);
+    }
+    if (!ok) return NTT256_ERR_PLAN;
     plan.id = ctx->next_plan_id++;
     it = ctx->plans.emplace(key, plan).first;
   }
