@@ -528,3 +528,19 @@ def test_zero_copy_host_buffers(torch_cuda, ctxs):
         assert np.array_equal(buf.reshape(-1, 8), got)
         ctx.inverse_host(buf, log_n, batch=batch, out=buf)
         assert np.array_equal(buf.reshape(-1, 8), x)
+
+
+def test_cpp_program_mirroring_the_reference_main(torch_cuda):
+    """tests/cpp/ref_flow_main.cpp re-creates the reference's self-checking main()
+    (big-num.cu:369-488: x[i] = i, CPU NTT, NTT_GPU_Naive, compare, NTT_GZKP, compare, sizes
+    2^5..) in C++ against include/ntt256_compat.hpp, which keeps the reference's driver
+    signatures.  Full 256-bit comparison, three fields, exit code 0 only without mismatches."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "ref_flow_main")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "tests", "cpp")])
+    out = subprocess.run([exe, "20"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "correct (0 mismatches)" in out.stdout
