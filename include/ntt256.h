@@ -131,6 +131,17 @@ int ntt256_fourstep_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, 
 int ntt256_fourstep_step1_peer(ntt256_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n, int log_r,
                                int log_p, int rank, ntt256_stream stream);
 
+/* Distributed INVERSE (includes the 1/n): consumes the output shards of the forward four-step
+ * (same log_r) and returns its input shards, i.e. it undoes steps 2, exchange, 1 with the same
+ * three-phase structure (local passes, exchange of contiguous chunks / fused peer stores, local
+ * passes); forward followed by inverse is the identity on every rank's shard. */
+int ntt256_fourstep_inverse_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                                  ntt256_stream stream);
+int ntt256_fourstep_inverse_step1_peer(ntt256_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n,
+                                       int log_r, int log_p, int rank, ntt256_stream stream);
+int ntt256_fourstep_inverse_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                                  ntt256_stream stream);
+
 /* Exchange buffers for the fused step: cudaMalloc'ed by the library so that a CUDA IPC handle
  * (64 bytes) describes exactly this buffer; the other ranks open it with THEIR device current. */
 int ntt256_ipc_alloc(int device, size_t bytes, void** d_ptr, unsigned char handle[64]);
@@ -145,7 +156,8 @@ int ntt256_enable_peer_access(int device, int peer_device);
  * ntt256_forward would run for 2^log_n points.  Returns the number of bytes needed
  * (including the NUL); writes at most buf_len bytes. */
 size_t ntt256_plan_describe(int log_n, int max_log_n, int tile_bits, int coalesce_bits, char* buf, size_t buf_len);
-/* Same for one local step (1 or 2) of the four-step decomposition on `rank`. */
+/* Same for one local step of the four-step decomposition on `rank`: 1, 2 = forward steps,
+ * 3, 4 = steps 1 and 2 of the distributed inverse. */
 size_t ntt256_plan_describe_fourstep(int step, int log_n, int log_r, int log_p, int rank, int max_log_n, int tile_bits,
                                      int coalesce_bits, char* buf, size_t buf_len);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */

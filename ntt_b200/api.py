@@ -168,6 +168,21 @@ class Ntt256:
         self._check(self._L.ntt256_fourstep_step2(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))
         return shard
 
+    def fourstep_inverse_step1(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None, peer_ptrs=None):
+        ptr = _device_ptr(shard, 1 << (log_n - log_p))
+        if peer_ptrs is None:
+            self._check(self._L.ntt256_fourstep_inverse_step1(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))
+        else:
+            arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(v) for v in peer_ptrs])
+            self._check(self._L.ntt256_fourstep_inverse_step1_peer(self._h, ptr, arr, log_n, log_r, log_p, rank,
+                                                                   _stream_handle(stream)))
+        return shard
+
+    def fourstep_inverse_step2(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        ptr = _device_ptr(shard, 1 << (log_n - log_p))
+        self._check(self._L.ntt256_fourstep_inverse_step2(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))
+        return shard
+
     # ---- host entry points (numpy in, numpy out, synchronous; H2D + transform + D2H)
     def forward_host(self, x: np.ndarray, log_n: int, batch: int = 1, out: Optional[np.ndarray] = None):
         return self._host(self._L.ntt256_forward_host, x, log_n, batch, out)

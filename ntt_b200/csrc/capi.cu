@@ -133,7 +133,7 @@ PlanRequest build_request(const PlanKey& key, int tile_bits, int coalesce_bits, 
   req.coalesce_bits = coalesce_bits;
   req.max_log_n = max_log_n;
   req.log_n = key.log_n;
-  if (key.kind != 0) {
+  if (key.kind == 1 || key.kind == 2) {
     const int L = key.log_n, lr = key.log_r, lp = key.log_p, lc = L - lr;
     const int nloc = L - lp;
     req.total_log_n = L;
@@ -161,6 +161,38 @@ PlanRequest build_request(const PlanKey& key, int tile_bits, int coalesce_bits, 
       for (int c = 0; c < lr - lp; ++c) req.target[lc - lp + c] = 64 + c;
       for (int i = 0; i < lp; ++i) req.target[lc - lp + lr - lp + i] = 64 + lr + i;
       req.time_hi = lc - 1;
+      req.time_lo = 0;
+      req.jlow_const = 0;
+    }
+  }
+  if (key.kind == 3 || key.kind == 4) {
+    // Distributed INVERSE that consumes the forward's output shards and returns the forward's
+    // input shards.  Its time index is K = k1 + R*k2 (the forward's frequency index), viewed as
+    // R' x C' with C' = 2^lr columns (K2 = k1) and R' = 2^lc rows (K1 = k2): the rank is again the
+    // top lp bits of the column index.  Local input layout = [k2 mod P][k1 local][k2 div P].
+    const int L = key.log_n, lr = key.log_r, lp = key.log_p, lc = L - lr;
+    const int nloc = L - lp;
+    req.total_log_n = L;
+    req.start.assign(nloc, 0);
+    req.target.assign(nloc, 0);
+    if (key.kind == 3) {
+      for (int i = 0; i < lc - lp; ++i) req.start[i] = lr + lp + i;              // k2 div P
+      for (int i = 0; i < lr - lp; ++i) req.start[lc - lp + i] = i;              // k1 local
+      for (int i = 0; i < lp; ++i) req.start[lc - lp + lr - lp + i] = lr + i;    // k2 mod P
+      // step 1 transforms K bits L-1 .. lr -> J bits 0 .. lc-1
+      for (int i = 0; i < lc - lp; ++i) req.target[i] = 64 + i;                  // j2 local, final
+      for (int i = 0; i < lr - lp; ++i) req.target[lc - lp + i] = i;             // k1 local waits
+      for (int i = 0; i < lp; ++i) req.target[lc - lp + lr - lp + i] = 64 + lc - lp + i;  // destination rank
+      req.time_hi = L - 1;
+      req.time_lo = lr;
+      req.jlow_const = (uint32_t)key.rank << (lr - lp);
+    } else {
+      for (int i = 0; i < lc - lp; ++i) req.start[i] = 64 + i;
+      for (int i = 0; i < lr - lp; ++i) req.start[lc - lp + i] = i;
+      for (int i = 0; i < lp; ++i) req.start[lc - lp + lr - lp + i] = lr - lp + i;  // the old rank bits
+      for (int i = 0; i < lc - lp; ++i) req.target[i] = 64 + i;
+      for (int m = 0; m < lr; ++m) req.target[lc - lp + m] = 64 + lc + m;           // j1 natural
+      req.time_hi = lr - 1;
       req.time_lo = 0;
       req.jlow_const = 0;
     }
@@ -700,11 +732,14 @@ int ntt256_coset_inverse(ntt256_ctx* ctx, void* d_data, int log_n, int batch, co
 
 static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log_r, int log_p, int rank,
                     cudaStream_t stream, const void* const* peer_recv = nullptr) {
+  const bool inverse = kind >= 3;
+  const bool first_step = (kind == 1 || kind == 3);
+  const int scale_log_n = (kind == 4) ? log_n : -1;
   if (!ctx || !d_shard || log_n > ctx->max_log_n || !fourstep_args_ok(log_n, log_r, log_p, rank)) return NTT256_ERR_ARG;
   CTX_CUDA(cudaSetDevice(ctx->device));
   const Plan* plan = nullptr;
   // step 2 does not depend on the rank (no foreign time bits remain)
-  int rc = get_plan(ctx, PlanKey{kind, log_n, log_r, log_p, kind == 1 ? rank : 0}, &plan);
+  int rc = get_plan(ctx, PlanKey{kind, log_n, log_r, log_p, first_step ? rank : 0}, &plan);
   if (rc) return rc;
   if (peer_recv && log_p > 0) {
     if (log_p > 3) return NTT256_ERR_ARG;
@@ -713,9 +748,23 @@ static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log
     ps.bits = log_p;
     ps.shift = log_n - 2 * log_p;  // local index bits below the destination-rank field
     ps.rank = rank;
-    return run_plan(ctx, *plan, d_shard, 0, 1, false, -1, stream, &ps);
+    return run_plan(ctx, *plan, d_shard, 0, 1, inverse, scale_log_n, stream, &ps);
   }
-  return run_plan(ctx, *plan, d_shard, 0, 1, false, -1, stream);
+  return run_plan(ctx, *plan, d_shard, 0, 1, inverse, scale_log_n, stream);
+}
+
+int ntt256_fourstep_inverse_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                                  ntt256_stream stream) {
+  return fourstep(ctx, 3, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream);
+}
+int ntt256_fourstep_inverse_step1_peer(ntt256_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n,
+                                       int log_r, int log_p, int rank, ntt256_stream stream) {
+  if (!peer_recv) return NTT256_ERR_ARG;
+  return fourstep(ctx, 3, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream, peer_recv);
+}
+int ntt256_fourstep_inverse_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                                  ntt256_stream stream) {
+  return fourstep(ctx, 4, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream);
 }
 
 int ntt256_fourstep_step1_peer(ntt256_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n, int log_r,
@@ -815,7 +864,7 @@ size_t ntt256_plan_describe_fourstep(int step, int log_n, int log_r, int log_p, 
                                      int coalesce_bits, char* buf, size_t buf_len) {
   std::string s;
   Plan plan;
-  if ((step != 1 && step != 2) || !fourstep_args_ok(log_n, log_r, log_p, rank) || max_log_n < log_n ||
+  if (step < 1 || step > 4 || !fourstep_args_ok(log_n, log_r, log_p, rank) || max_log_n < log_n ||
       !make_plan(build_request(PlanKey{step, log_n, log_r, log_p, rank}, tile_bits, coalesce_bits, max_log_n), &plan))
     s = "{\"error\": \"no plan\"}";
   else

@@ -46,6 +46,24 @@ def gather_output(shards: list[np.ndarray], log_n: int, world: int, log_r: int |
     return np.ascontiguousarray(m).reshape(-1, 8)
 
 
+def scatter_output_layout(X: np.ndarray, log_n: int, world: int, log_r: int | None = None) -> list[np.ndarray]:
+    """Natural-order X -> shards in the forward's OUTPUT layout (inverse of gather_output): the input
+    of FourStep.inverse()."""
+    log_r = default_log_r(log_n) if log_r is None else log_r
+    R, C = 1 << log_r, 1 << (log_n - log_r)
+    P = world
+    m = X.reshape(C // P, P, P, R // P, 8)           # [k2_high][k2_low][rank][k1_local]
+    m = m.transpose(2, 1, 3, 0, 4)                   # [rank][k2_low][k1_local][k2_high]
+    return [np.ascontiguousarray(m[r]).reshape(-1, 8) for r in range(world)]
+
+
+def gather_input_layout(shards: list[np.ndarray], log_n: int, world: int, log_r: int | None = None) -> np.ndarray:
+    """Shards in the forward's INPUT layout (column blocks) -> natural order (inverse of scatter_input)."""
+    log_r = default_log_r(log_n) if log_r is None else log_r
+    R, C = 1 << log_r, 1 << (log_n - log_r)
+    return np.ascontiguousarray(np.concatenate([s.reshape(R, C // world, 8) for s in shards], axis=1)).reshape(-1, 8)
+
+
 def shard_batch(batch: int, world: int, rank: int) -> tuple[int, int]:
     """Transforms [lo, hi) of a batch handled by `rank` (independent units, no collective)."""
     per = (batch + world - 1) // world
@@ -191,6 +209,27 @@ class FourStep:
                 lib().ntt256_ipc_free(self._dev, p)
             self._opened, self._owned, self._peers = [], [], None
             self.a = self.b = None
+
+    def inverse(self):
+        """Distributed inverse (with 1/n): consumes shards in the forward's OUTPUT layout and
+        leaves shards in the forward's INPUT layout, so forward() then inverse() is the identity."""
+        import torch.distributed as dist
+
+        ctx = self.ctx
+        if self.fused:
+            src, dst = (self.a, self.b) if self._cur == 0 else (self.b, self.a)
+            ctx.fourstep_inverse_step1(src, self.log_n, self.log_r, self.log_p, self.rank,
+                                       peer_ptrs=self._peers[1 - self._cur])
+            dist.all_reduce(self._flag, group=self.group)
+            ctx.fourstep_inverse_step2(dst, self.log_n, self.log_r, self.log_p, self.rank)
+            self._cur = 1 - self._cur
+            return dst
+        ctx.fourstep_inverse_step1(self.a, self.log_n, self.log_r, self.log_p, self.rank)
+        if self.world > 1:
+            dist.all_to_all_single(self.b, self.a, group=self.group)
+            self.a, self.b = self.b, self.a
+        ctx.fourstep_inverse_step2(self.a, self.log_n, self.log_r, self.log_p, self.rank)
+        return self.a
 
     def forward(self):
         """One distributed transform.  The result shard is returned (and becomes the input of the

@@ -19,6 +19,7 @@ EXPORTS = [
     "ntt256_ctx_set_stream_twiddle_limit",
     "ntt256_forward", "ntt256_inverse", "ntt256_forward_batch", "ntt256_inverse_batch",
     "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2", "ntt256_fourstep_step1_peer", "ntt256_enable_peer_access",
+    "ntt256_fourstep_inverse_step1", "ntt256_fourstep_inverse_step1_peer", "ntt256_fourstep_inverse_step2",
     "ntt256_ipc_alloc", "ntt256_ipc_open", "ntt256_ipc_close", "ntt256_ipc_free",
     "ntt256_vec_mul", "ntt256_to_montgomery", "ntt256_from_montgomery", "ntt256_coset_forward",
     "ntt256_coset_inverse",
@@ -56,8 +57,10 @@ def lib() -> ctypes.CDLL:
             getattr(L, name).argtypes = [vp, vp, ci, ci, vp]
         for name in ("ntt256_forward_host", "ntt256_inverse_host"):
             getattr(L, name).argtypes = [vp, vp, vp, ci, ci]
-        for name in ("ntt256_fourstep_step1", "ntt256_fourstep_step2"):
+        for name in ("ntt256_fourstep_step1", "ntt256_fourstep_step2", "ntt256_fourstep_inverse_step1",
+                     "ntt256_fourstep_inverse_step2"):
             getattr(L, name).argtypes = [vp, vp, ci, ci, ci, ci, vp]
+        L.ntt256_fourstep_inverse_step1_peer.argtypes = [vp, vp, ctypes.POINTER(vp), ci, ci, ci, ci, vp]
         L.ntt256_fourstep_step1_peer.argtypes = [vp, vp, ctypes.POINTER(vp), ci, ci, ci, ci, vp]
         L.ntt256_vec_mul.argtypes = [vp, vp, vp, vp, ctypes.c_ulonglong, ci, vp]
         for name in ("ntt256_to_montgomery", "ntt256_from_montgomery"):

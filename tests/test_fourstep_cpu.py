@@ -71,6 +71,44 @@ def test_fused_peer_store_equals_all_to_all(built, log_n, log_r, world):
         assert recv[r] == co.array_to_ints(want[r])
 
 
+@pytest.mark.parametrize("log_n,log_r,world,T,g", [(8, 4, 2, 5, 1), (10, 5, 4, 6, 1), (9, 5, 1, 5, 1), (11, 6, 8, 6, 1), (10, 6, 2, 8, 2)])
+def test_distributed_inverse_undoes_the_forward_layouts(built, log_n, log_r, world, T, g):
+    """Inverse four-step (plan kinds 3, 4): input = the forward's OUTPUT shards, output = the
+    forward's INPUT shards, values = the oracle's inverse NTT."""
+    F = po.BLS12_381_FR
+    log_p = world.bit_length() - 1
+    rng = random.Random(11 * log_n + world)
+    x = [rng.randrange(F.p) for _ in range(1 << log_n)]
+    X = po.ntt_ref(x, F)
+    shards = nd.scatter_output_layout(co.ints_to_array(X), log_n, world, log_r)
+    assert np.array_equal(nd.gather_output(shards, log_n, world, log_r), co.ints_to_array(X))
+    w_max = pow(F.g, (F.p - 1) >> 12, F.p)
+    scale = pow(1 << log_n, F.p - 2, F.p)
+
+    def run(step, arr, rank):
+        plan = plan_describe_fourstep(step, log_n, log_r, log_p, rank, 12, T, g)
+        assert "error" not in plan
+        data = co.array_to_ints(arr)
+        for i, pd in enumerate(plan["passes"]):
+            pd = dict(pd)
+            sc = None
+            if step == 4 and i == len(plan["passes"]) - 1:
+                sc = scale
+                if pd["nrounds"] >= 2:
+                    pd["scaled_round"] = 0
+                else:
+                    pd["scale_out"] = 1
+            plan_sim.run_pass(data, pd, F.p, w_max, 12, inverse=True, scale=sc)
+        return co.ints_to_array(data)
+
+    s1 = [run(3, s, r) for r, s in enumerate(shards)]
+    recv = nd.exchange_reference(s1, world)
+    s2 = [run(4, s, r) for r, s in enumerate(recv)]
+    assert co.array_to_ints(nd.gather_input_layout(s2, log_n, world, log_r)) == x
+    for r in range(world):
+        assert np.array_equal(s2[r], nd.scatter_input(co.ints_to_array(x), log_n, world, log_r)[r])
+
+
 def test_scatter_gather_are_inverse_views():
     log_n, world = 8, 4
     x = np.arange((1 << log_n) * 8, dtype=np.uint32).reshape(-1, 8)

@@ -544,3 +544,35 @@ def test_cpp_program_mirroring_the_reference_main(torch_cuda):
     out = subprocess.run([exe, "20"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "correct (0 mismatches)" in out.stdout
+
+
+@pytest.mark.parametrize("log_n,world", [(12, 1), (16, 2), (20, 8), (21, 4)])
+def test_distributed_inverse_ranks_emulated_on_one_gpu(torch_cuda, ctxs, log_n, world):
+    """Inverse four-step on the forward's output shards must return the forward's input shards
+    (values = oracle inverse NTT), every rank emulated on this GPU, exchange by its host definition."""
+    from ntt_b200 import dist as nd
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 24)
+    log_p, log_r = world.bit_length() - 1, nd.default_log_r(log_n)
+    x = co.splitmix_elements(1 << log_n, p, 0x4E5454 + 70 + log_n)
+    X = co.ntt(x, p, g, threads=8)
+    s1 = []
+    for r, sh in enumerate(nd.scatter_output_layout(X, log_n, world, log_r)):
+        d = torch.from_numpy(sh.view(np.int32)).cuda().view(-1)
+        ctx.fourstep_inverse_step1(d, log_n, log_r, log_p, r)
+        torch.cuda.synchronize()
+        s1.append(d.cpu().numpy().view(np.uint32).reshape(-1, 8))
+    outs = []
+    for r, sh in enumerate(nd.exchange_reference(s1, world)):
+        d = torch.from_numpy(np.ascontiguousarray(sh).view(np.int32)).cuda().view(-1)
+        ctx.fourstep_inverse_step2(d, log_n, log_r, log_p, r)
+        torch.cuda.synchronize()
+        outs.append(d.cpu().numpy().view(np.uint32).reshape(-1, 8))
+    want = nd.scatter_input(x, log_n, world, log_r)
+    for r in range(world):
+        assert np.array_equal(outs[r], want[r]), r
+    assert np.array_equal(nd.gather_input_layout(outs, log_n, world, log_r), x)

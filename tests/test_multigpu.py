@@ -33,9 +33,14 @@ for fused in (False, True):
     if rank == 0:
         X = nd.gather_output([t.cpu().numpy().view(np.uint32).reshape(-1, 8) for t in gathered], log_n, world)
         assert np.array_equal(X, co.ntt(x, p, g, threads=8)), f"four-step 2^{log_n} over {world} GPUs (fused={fused}) differs from the oracle"
-    # second call reuses the ping-pong buffers: transform of the previous output
+    # distributed inverse consumes the forward's output shards and must return the input shard
+    back = fs.inverse().clone()
+    torch.cuda.synchronize()
+    assert np.array_equal(back.cpu().numpy().view(np.uint32).reshape(-1, 8), shard), f"inverse(forward(shard)) != shard (fused={fused}, 2^{log_n})"
+    # another forward reuses the ping-pong buffers
     out2 = fs.forward().clone()
     torch.cuda.synchronize()
+    assert torch.equal(out2, out)
     dist.barrier()
     if fused:
         fs.close()
