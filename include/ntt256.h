@@ -142,6 +142,21 @@ int ntt256_fourstep_inverse_step1_peer(ntt256_ctx* ctx, void* d_shard, const voi
 int ntt256_fourstep_inverse_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
                                   ntt256_stream stream);
 
+/* ---- single-process multi-GPU driver (the C-ABI list of SURVEY.md par. 8b): one host thread
+ * drives ngpus (power of two, <= 8) peer-connected devices; no NCCL, no second process.  Shards
+ * use the four-step layouts above (default log_r = ceil(log_n/2)); the exchange is the fused one
+ * (phase 1's last kernel stores into the peers' receive buffers), phases are ordered with
+ * cross-device events, and phase 2's last kernel writes the result back into d_shards[i].
+ * Calls are asynchronous on internal streams: ntt256_mgpu_synchronize() waits for them.
+ * devices == NULL selects devices 0 .. ngpus-1. */
+typedef struct ntt256_mgpu ntt256_mgpu;
+int ntt256_mgpu_create(ntt256_mgpu** out, int ngpus, const int* devices, int field, int max_log_n);
+int ntt256_mgpu_forward(ntt256_mgpu* m, void* const* d_shards, int log_n);
+int ntt256_mgpu_inverse(ntt256_mgpu* m, void* const* d_shards, int log_n);  /* undoes ntt256_mgpu_forward */
+int ntt256_mgpu_forward_batch(ntt256_mgpu* m, void* const* d_shards, int log_n, int batch_per_gpu);
+int ntt256_mgpu_synchronize(ntt256_mgpu* m);
+void ntt256_mgpu_destroy(ntt256_mgpu* m);
+
 /* Exchange buffers for the fused step: cudaMalloc'ed by the library so that a CUDA IPC handle
  * (64 bytes) describes exactly this buffer; the other ranks open it with THEIR device current. */
 int ntt256_ipc_alloc(int device, size_t bytes, void** d_ptr, unsigned char handle[64]);

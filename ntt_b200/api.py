@@ -241,3 +241,57 @@ def NTT_GPU_Naive(data, length: int, reverse=None, reverse_len: int = 0, prime=N
     """Drop-in for NTT_GPU_Naive<8,256> (big-num.cu:106-170): same contract and same results as
     NTT_GZKP (the reference checks both against the same CPU output, big-num.cu:439-467)."""
     return NTT_GZKP(data, length, reverse, reverse_len, prime, omega, 0, 0, stream)
+
+
+class Ntt256MultiGpu:
+    """ntt256_mgpu: one host thread driving several peer-connected GPUs (no NCCL, no extra
+    processes).  Shards are torch CUDA tensors, one per device, in the four-step layouts of
+    ntt_b200.dist (scatter_input / gather_output)."""
+
+    def __init__(self, ngpus: int, field: str = "bn254_fr", max_log_n: int = 24, devices: Optional[Sequence[int]] = None):
+        from .lib import FIELD_BLS12_381_FR, FIELD_BN254_FR
+
+        self._L = _load_lib()
+        self._h = ctypes.c_void_p()
+        fid = {"bn254_fr": FIELD_BN254_FR, "bls12_381_fr": FIELD_BLS12_381_FR}[field]
+        devs = (ctypes.c_int * ngpus)(*devices) if devices is not None else None
+        rc = self._L.ntt256_mgpu_create(ctypes.byref(self._h), ngpus, devs, fid, max_log_n)
+        if rc:
+            raise Ntt256Error(rc)
+        self.ngpus = ngpus
+
+    def _ptrs(self, shards, n_elements):
+        if len(shards) != self.ngpus:
+            raise ValueError("one shard per GPU")
+        return (ctypes.c_void_p * self.ngpus)(*[_device_ptr(s, n_elements) for s in shards])
+
+    def forward(self, shards, log_n: int):
+        rc = self._L.ntt256_mgpu_forward(self._h, self._ptrs(shards, (1 << log_n) // self.ngpus), log_n)
+        if rc:
+            raise Ntt256Error(rc)
+
+    def inverse(self, shards, log_n: int):
+        rc = self._L.ntt256_mgpu_inverse(self._h, self._ptrs(shards, (1 << log_n) // self.ngpus), log_n)
+        if rc:
+            raise Ntt256Error(rc)
+
+    def forward_batch(self, shards, log_n: int, batch_per_gpu: int):
+        rc = self._L.ntt256_mgpu_forward_batch(self._h, self._ptrs(shards, batch_per_gpu << log_n), log_n, batch_per_gpu)
+        if rc:
+            raise Ntt256Error(rc)
+
+    def synchronize(self):
+        rc = self._L.ntt256_mgpu_synchronize(self._h)
+        if rc:
+            raise Ntt256Error(rc)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.ntt256_mgpu_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

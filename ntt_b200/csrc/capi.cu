@@ -731,7 +731,7 @@ int ntt256_coset_inverse(ntt256_ctx* ctx, void* d_data, int log_n, int batch, co
 }
 
 static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log_r, int log_p, int rank,
-                    cudaStream_t stream, const void* const* peer_recv = nullptr) {
+                    cudaStream_t stream, const void* const* peer_recv = nullptr, const IoSpec* io = nullptr) {
   const bool inverse = kind >= 3;
   const bool first_step = (kind == 1 || kind == 3);
   const int scale_log_n = (kind == 4) ? log_n : -1;
@@ -748,9 +748,9 @@ static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log
     ps.bits = log_p;
     ps.shift = log_n - 2 * log_p;  // local index bits below the destination-rank field
     ps.rank = rank;
-    return run_plan(ctx, *plan, d_shard, 0, 1, inverse, scale_log_n, stream, &ps);
+    return run_plan(ctx, *plan, d_shard, 0, 1, inverse, scale_log_n, stream, &ps, io);
   }
-  return run_plan(ctx, *plan, d_shard, 0, 1, inverse, scale_log_n, stream);
+  return run_plan(ctx, *plan, d_shard, 0, 1, inverse, scale_log_n, stream, nullptr, io);
 }
 
 int ntt256_fourstep_inverse_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
@@ -780,6 +780,140 @@ int ntt256_fourstep_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, 
 int ntt256_fourstep_step2(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
                           ntt256_stream stream) {
   return fourstep(ctx, 2, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- single-process multi-GPU driver
+struct ntt256_mgpu {
+  int P = 0, log_p = 0, max_log_n = 0;
+  std::vector<int> dev;
+  std::vector<ntt256_ctx*> ctx;
+  std::vector<void*> recv;
+  size_t recv_bytes = 0;
+  std::vector<cudaStream_t> stream;
+  std::vector<cudaEvent_t> ev1, ev2;
+  bool ev2_valid = false;
+};
+
+void ntt256_mgpu_destroy(ntt256_mgpu* m) {
+  if (!m) return;
+  for (int i = 0; i < (int)m->dev.size(); ++i) {
+    cudaSetDevice(m->dev[i]);
+    cudaDeviceSynchronize();
+    if (i < (int)m->recv.size() && m->recv[i]) cudaFree(m->recv[i]);
+    if (i < (int)m->stream.size() && m->stream[i]) cudaStreamDestroy(m->stream[i]);
+    if (i < (int)m->ev1.size() && m->ev1[i]) cudaEventDestroy(m->ev1[i]);
+    if (i < (int)m->ev2.size() && m->ev2[i]) cudaEventDestroy(m->ev2[i]);
+    if (i < (int)m->ctx.size() && m->ctx[i]) ntt256_ctx_destroy(m->ctx[i]);
+  }
+  delete m;
+}
+
+int ntt256_mgpu_create(ntt256_mgpu** out, int ngpus, const int* devices, int field, int max_log_n) {
+  if (!out || ngpus < 1 || ngpus > 8 || (ngpus & (ngpus - 1))) return NTT256_ERR_ARG;
+  *out = nullptr;
+  ntt256_mgpu* m = new (std::nothrow) ntt256_mgpu();
+  if (!m) return NTT256_ERR_NOMEM;
+  m->P = ngpus;
+  while ((1 << m->log_p) < ngpus) ++m->log_p;
+  m->max_log_n = max_log_n;
+  m->dev.resize(ngpus);
+  m->ctx.assign(ngpus, nullptr);
+  m->recv.assign(ngpus, nullptr);
+  m->stream.assign(ngpus, nullptr);
+  m->ev1.assign(ngpus, nullptr);
+  m->ev2.assign(ngpus, nullptr);
+  for (int i = 0; i < ngpus; ++i) m->dev[i] = devices ? devices[i] : i;
+  for (int i = 0; i < ngpus; ++i) {
+    int rc = ntt256_ctx_create_named(&m->ctx[i], m->dev[i], field, max_log_n);
+    if (rc) {
+      ntt256_mgpu_destroy(m);
+      return rc;
+    }
+    if (cudaSetDevice(m->dev[i]) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&m->stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev1[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev2[i], cudaEventDisableTiming) != cudaSuccess) {
+      ntt256_mgpu_destroy(m);
+      return NTT256_ERR_CUDA;
+    }
+    for (int j = 0; j < ngpus; ++j)
+      if (j != i && ntt256_enable_peer_access(m->dev[i], m->dev[j]) != NTT256_OK) {
+        ntt256_mgpu_destroy(m);
+        return NTT256_ERR_CUDA;
+      }
+  }
+  *out = m;
+  return NTT256_OK;
+}
+
+static int mgpu_transform(ntt256_mgpu* m, void* const* d_shards, int log_n, bool inverse) {
+  if (!m || !d_shards || log_n > m->max_log_n) return NTT256_ERR_ARG;
+  const int P = m->P, lp = m->log_p;
+  const int lr = (log_n + 1) / 2;
+  if (!fourstep_args_ok(log_n, lr, lp, 0)) return NTT256_ERR_ARG;
+  for (int i = 0; i < P; ++i)
+    if (!d_shards[i]) return NTT256_ERR_ARG;
+  const size_t bytes = (size_t)32 << (log_n - lp);
+  if (bytes > m->recv_bytes) {
+    for (int i = 0; i < P; ++i) {
+      if (cudaSetDevice(m->dev[i]) != cudaSuccess) return NTT256_ERR_CUDA;
+      cudaDeviceSynchronize();
+      if (m->recv[i]) cudaFree(m->recv[i]);
+      m->recv[i] = nullptr;
+      if (cudaMalloc(&m->recv[i], bytes) != cudaSuccess) return NTT256_ERR_NOMEM;
+    }
+    m->recv_bytes = bytes;
+    m->ev2_valid = false;
+  }
+  const int k1 = inverse ? 3 : 1, k2 = inverse ? 4 : 2;
+  // phase 1: every device runs its local passes; the last one stores into the peers' receive buffers
+  for (int i = 0; i < P; ++i) {
+    if (cudaSetDevice(m->dev[i]) != cudaSuccess) return NTT256_ERR_CUDA;
+    if (m->ev2_valid)  // the previous transform's phase 2 may still be reading the receive buffers
+      for (int j = 0; j < P; ++j) cudaStreamWaitEvent(m->stream[i], m->ev2[j], 0);
+    int rc = fourstep(m->ctx[i], k1, d_shards[i], log_n, lr, lp, i, m->stream[i], P > 1 ? m->recv.data() : nullptr);
+    if (rc) return rc;
+    if (cudaEventRecord(m->ev1[i], m->stream[i]) != cudaSuccess) return NTT256_ERR_CUDA;
+  }
+  // phase 2: after every device's phase 1 has finished, local passes on the received data; the
+  // last pass writes the result into the caller's shard buffer
+  for (int i = 0; i < P; ++i) {
+    if (cudaSetDevice(m->dev[i]) != cudaSuccess) return NTT256_ERR_CUDA;
+    for (int j = 0; j < P; ++j) cudaStreamWaitEvent(m->stream[i], m->ev1[j], 0);
+    int rc;
+    if (P > 1) {
+      IoSpec io;
+      io.dst_last = d_shards[i];
+      rc = fourstep(m->ctx[i], k2, m->recv[i], log_n, lr, lp, i, m->stream[i], nullptr, &io);
+    } else {
+      rc = fourstep(m->ctx[i], k2, d_shards[i], log_n, lr, lp, i, m->stream[i]);
+    }
+    if (rc) return rc;
+    if (cudaEventRecord(m->ev2[i], m->stream[i]) != cudaSuccess) return NTT256_ERR_CUDA;
+  }
+  m->ev2_valid = true;
+  return NTT256_OK;
+}
+
+int ntt256_mgpu_forward(ntt256_mgpu* m, void* const* d_shards, int log_n) { return mgpu_transform(m, d_shards, log_n, false); }
+int ntt256_mgpu_inverse(ntt256_mgpu* m, void* const* d_shards, int log_n) { return mgpu_transform(m, d_shards, log_n, true); }
+
+int ntt256_mgpu_forward_batch(ntt256_mgpu* m, void* const* d_shards, int log_n, int batch_per_gpu) {
+  if (!m || !d_shards || batch_per_gpu < 1) return NTT256_ERR_ARG;
+  for (int i = 0; i < m->P; ++i) {
+    int rc = transform(m->ctx[i], d_shards[i], log_n, batch_per_gpu, false, m->stream[i]);
+    if (rc) return rc;
+  }
+  return NTT256_OK;
+}
+
+int ntt256_mgpu_synchronize(ntt256_mgpu* m) {
+  if (!m) return NTT256_ERR_ARG;
+  for (int i = 0; i < m->P; ++i) {
+    if (cudaSetDevice(m->dev[i]) != cudaSuccess) return NTT256_ERR_CUDA;
+    if (cudaStreamSynchronize(m->stream[i]) != cudaSuccess) return NTT256_ERR_CUDA;
+  }
+  return NTT256_OK;
 }
 
 int ntt256_ipc_alloc(int device, size_t bytes, void** d_ptr, unsigned char handle[64]) {

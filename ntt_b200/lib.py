@@ -21,6 +21,8 @@ EXPORTS = [
     "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2", "ntt256_fourstep_step1_peer", "ntt256_enable_peer_access",
     "ntt256_fourstep_inverse_step1", "ntt256_fourstep_inverse_step1_peer", "ntt256_fourstep_inverse_step2",
     "ntt256_ipc_alloc", "ntt256_ipc_open", "ntt256_ipc_close", "ntt256_ipc_free",
+    "ntt256_mgpu_create", "ntt256_mgpu_forward", "ntt256_mgpu_inverse", "ntt256_mgpu_forward_batch",
+    "ntt256_mgpu_synchronize", "ntt256_mgpu_destroy",
     "ntt256_vec_mul", "ntt256_to_montgomery", "ntt256_from_montgomery", "ntt256_coset_forward",
     "ntt256_coset_inverse",
     "ntt256_plan_describe", "ntt256_plan_describe_fourstep", "ntt256_launch_count", "ntt256_strerror", "ntt256_last_cuda_error",
@@ -68,6 +70,13 @@ def lib() -> ctypes.CDLL:
         for name in ("ntt256_coset_forward", "ntt256_coset_inverse"):
             getattr(L, name).argtypes = [vp, vp, ci, ci, u32p, vp]
         L.ntt256_enable_peer_access.argtypes = [ci, ci]
+        L.ntt256_mgpu_create.argtypes = [ctypes.POINTER(vp), ci, ctypes.POINTER(ci), ci, ci]
+        L.ntt256_mgpu_forward.argtypes = [vp, ctypes.POINTER(vp), ci]
+        L.ntt256_mgpu_inverse.argtypes = [vp, ctypes.POINTER(vp), ci]
+        L.ntt256_mgpu_forward_batch.argtypes = [vp, ctypes.POINTER(vp), ci, ci]
+        L.ntt256_mgpu_synchronize.argtypes = [vp]
+        L.ntt256_mgpu_destroy.argtypes = [vp]
+        L.ntt256_mgpu_destroy.restype = None
         L.ntt256_ipc_alloc.argtypes = [ci, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
         L.ntt256_ipc_open.argtypes = [ci, ctypes.c_char_p, ctypes.POINTER(vp)]
         L.ntt256_ipc_close.argtypes = [ci, vp]

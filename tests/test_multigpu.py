@@ -78,3 +78,48 @@ def test_fourstep_and_batch_over_nccl(tmp_path):
          "127.0.0.1", "--master-port", "29631", str(script)], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, (out.stdout[-1500:] + out.stderr[-3000:])
     assert "MULTIGPU_OK" in out.stdout
+
+
+def test_single_process_mgpu_driver():
+    """ntt256_mgpu_*: one host thread, all GPUs of the box, fused peer-store exchange ordered by
+    cross-device events.  Forward equals the oracle, inverse restores the input shards, batches run
+    independently per GPU."""
+    import numpy as np
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("needs CUDA")
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("single-GPU box")
+    world = 1 << (n.bit_length() - 1)
+    sys.path.insert(0, ROOT)
+    from ntt_b200 import dist as nd
+    from ntt_b200.api import FIELDS, Ntt256MultiGpu
+    from oracle import c_oracle as co
+
+    p, g = FIELDS["bn254_fr"]
+    mg = Ntt256MultiGpu(world, "bn254_fr", max_log_n=22)
+    for log_n in (12, 20, 21):
+        x = co.splitmix_elements(1 << log_n, p, 555 + log_n)
+        host = nd.scatter_input(x, log_n, world)
+        shards = [torch.from_numpy(h.view(np.int32)).to(f"cuda:{i}").view(-1) for i, h in enumerate(host)]
+        for rep in range(2):  # twice: buffers and events are reused
+            mg.forward(shards, log_n)
+            mg.synchronize()
+            outs = [s.cpu().numpy().view(np.uint32).reshape(-1, 8) for s in shards]
+            assert np.array_equal(nd.gather_output(outs, log_n, world), co.ntt(x, p, g, threads=8)), (log_n, rep)
+            mg.inverse(shards, log_n)
+            mg.synchronize()
+            for i in range(world):
+                assert np.array_equal(shards[i].cpu().numpy().view(np.uint32).reshape(-1, 8), host[i]), (log_n, rep, i)
+    log_n, per = 12, 3
+    xs = [co.splitmix_elements(per << log_n, p, 900 + i) for i in range(world)]
+    shards = [torch.from_numpy(h.view(np.int32)).to(f"cuda:{i}").view(-1) for i, h in enumerate(xs)]
+    mg.forward_batch(shards, log_n, per)
+    mg.synchronize()
+    for i in range(world):
+        got = shards[i].cpu().numpy().view(np.uint32).reshape(-1, 8)
+        for b in range(per):
+            assert np.array_equal(got[b << log_n:(b + 1) << log_n], co.ntt(xs[i][b << log_n:(b + 1) << log_n], p, g))
+    mg.close()
