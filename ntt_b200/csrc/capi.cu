@@ -272,6 +272,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
         table_scale_kernel<<<(unsigned)((count + 127) / 128), 128, 0, stream>>>(tab, ctx->loc, count, ctx->fp, c);
         ++ctx->launches;
         CTX_CUDA(cudaGetLastError());
+        CTX_CUDA(cudaStreamSynchronize(stream));  // one-off: later calls may use other streams
         it = ctx->loc_scaled.emplace(scale_log_n, tab).first;
       }
       loc_scaled = it->second;
@@ -309,6 +310,8 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
             ntt_pass_kernel<<<ggrid, 1u << (Tg - 3), (size_t)32 << Tg, stream>>>((const uint4*)d_data, (uint4*)d_data, G);
             ++ctx->launches;
             CTX_CUDA(cudaGetLastError());
+            // one-off: the array may be read from other streams by later calls
+            CTX_CUDA(cudaStreamSynchronize(stream));
             ts = ctx->tw_streams.emplace(tkey, tab).first;
           } else {
             cudaGetLastError();  // not enough memory: keep the two-lookup path

@@ -576,3 +576,33 @@ def test_distributed_inverse_ranks_emulated_on_one_gpu(torch_cuda, ctxs, log_n, 
     for r in range(world):
         assert np.array_equal(outs[r], want[r]), r
     assert np.array_equal(nd.gather_input_layout(outs, log_n, world, log_r), x)
+
+
+def test_repeated_runs_are_bitwise_identical(torch_cuda, ctxs):
+    """Race smoke test (compute-sanitizer is closed on this pool): many repetitions under several
+    tilings, streams in flight concurrently, must reproduce the oracle every time."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = Ntt256("bn254_fr", max_log_n=20)
+    for tile_bits, coalesce_bits in ((11, 2), (9, 1), (12, 3)):
+        ctx.set_tuning(tile_bits, coalesce_bits)
+        for log_n in (13, 17, 20):
+            x = co.splitmix_elements(1 << log_n, p, 8080 + log_n)
+            want = torch.from_numpy(co.ntt(x, p, g, threads=8).view(np.int32)).cuda().view(-1)
+            src = torch.from_numpy(x.view(np.int32)).cuda().view(-1)
+            streams = [torch.cuda.Stream() for _ in range(3)]
+            bufs = [torch.empty_like(src) for _ in range(3)]
+            bad = 0
+            for rep in range(12):
+                for s, b in zip(streams, bufs):
+                    s.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(s):
+                        b.copy_(src)
+                        ctx.forward(b, log_n)
+                        bad += int(not torch.equal(b, want))
+            torch.cuda.synchronize()
+            assert bad == 0, (tile_bits, log_n, bad)
+    ctx.close()
