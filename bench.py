@@ -200,7 +200,7 @@ def run_ours(args):
     else:
         from ntt_b200.dist import FourStep
 
-        fs = FourStep(ctx, LOG_N, world, rank, fused=not args.no_fused)
+        fs = FourStep(ctx, LOG_N, world, rank, fused=not args.no_fused, log_r=(args.log_r or None))
         x_shard = c_oracle.splitmix_elements(n // world, p, 0x4E5454 + 100 + rank)
         fs.load_shard(torch.from_numpy(x_shard.view(np.int32)).cuda())
 
@@ -354,6 +354,7 @@ def main():
     ap.add_argument("--coalesce-bits", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of fused peer stores")
+    ap.add_argument("--log-r", type=int, default=0, help="multi-GPU: rows = 2^log_r of the four-step view (0: automatic)")
     ap.add_argument("--log-n", type=int, default=24, help="transform size (default: the BASELINE metric's 2^24)")
     args = ap.parse_args()
     if args.log_n != 24:
