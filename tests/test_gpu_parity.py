@@ -606,3 +606,27 @@ def test_repeated_runs_are_bitwise_identical(torch_cuda, ctxs):
             torch.cuda.synchronize()
             assert bad == 0, (tile_bits, log_n, bad)
     ctx.close()
+
+
+def test_2p26_properties(torch_cuda):
+    """A transform beyond the streamed-twiddle limit (two-factor first pass, 5 passes, 2 GiB of
+    data): one output sampled by Horner on the CPU, and the round trip on the device."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = Ntt256("bn254_fr", max_log_n=26)
+    log_n = 26
+    x = co.splitmix_elements(1 << log_n, p, 2626)
+    src = torch.from_numpy(x.view(np.int32)).cuda().view(-1)
+    d = src.clone()
+    ctx.forward(d, log_n)
+    torch.cuda.synchronize()
+    k = (1 << 25) + 12345
+    got = d[8 * k: 8 * k + 8].cpu().numpy().view(np.uint32)
+    assert co.dft_sample(x, p, g, k) == sum(int(got[i]) << (32 * i) for i in range(8))
+    ctx.inverse(d, log_n)
+    torch.cuda.synchronize()
+    assert torch.equal(d, src)
+    ctx.close()
