@@ -344,7 +344,7 @@ def run_ours(args):
 
 
 def main():
-    global LOG_N, METRIC
+    global LOG_N, METRIC, FIELD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -355,8 +355,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of fused peer stores")
     ap.add_argument("--log-r", type=int, default=0, help="multi-GPU: rows = 2^log_r of the four-step view (0: automatic)")
+    ap.add_argument("--field", default="bn254_fr", choices=["bn254_fr", "bls12_381_fr"])
     ap.add_argument("--log-n", type=int, default=24, help="transform size (default: the BASELINE metric's 2^24)")
     args = ap.parse_args()
+    FIELD = args.field
     if args.log_n != 24:
         LOG_N = args.log_n
         METRIC = f"ntt256_elements_per_s_2^{LOG_N}"
