@@ -71,6 +71,14 @@ int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits);
  * built on first use, kept in the context).  Arrays up to max_bytes are built automatically
  * (default 1 GiB, i.e. n <= 2^25); 0 selects the two-lookup path always. */
 int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes);
+/* Calls with batch * 2^log_n <= max_elements (default 2^17) are latency-bound and run on the
+ * four-elements-per-thread kernel, those of at most half that on the two-elements-per-thread
+ * kernel (more, shorter threads); 0 keeps every call on the throughput kernel. */
+int ntt256_ctx_set_small_transform_limit(ntt256_ctx* ctx, long long max_elements);
+/* Tuning/testing: force the pass kernel that keeps 2^log2_elements (1, 2 or 3) elements per thread
+ * for ntt256_forward/inverse[_batch]; 0 restores the automatic choice.  Tiles are limited to 2^11
+ * elements below 3. */
+int ntt256_ctx_set_elements_per_thread(ntt256_ctx* ctx, int log2_elements);
 
 /* Forward NTT of 2^log_n points, in place on device memory, natural order in and out.
  * == NTT_GZKP<8,256>(data, 1<<log_n, ..., prime, omega, B, G)  (big-num.cu:458). */
@@ -171,6 +179,10 @@ int ntt256_enable_peer_access(int device, int peer_device);
  * ntt256_forward would run for 2^log_n points.  Returns the number of bytes needed
  * (including the NUL); writes at most buf_len bytes. */
 size_t ntt256_plan_describe(int log_n, int max_log_n, int tile_bits, int coalesce_bits, char* buf, size_t buf_len);
+/* group_bits = 3: the throughput kernel (eight elements per thread); 2: the four-elements-per-thread
+ * kernel the library picks for small, latency-bound transforms. */
+size_t ntt256_plan_describe_ex(int log_n, int max_log_n, int tile_bits, int coalesce_bits, int group_bits, char* buf,
+                               size_t buf_len);
 /* Same for one local step of the four-step decomposition on `rank`: 1, 2 = forward steps,
  * 3, 4 = steps 1 and 2 of the distributed inverse. */
 size_t ntt256_plan_describe_fourstep(int step, int log_n, int log_r, int log_p, int rank, int max_log_n, int tile_bits,

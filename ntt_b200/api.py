@@ -100,6 +100,14 @@ class Ntt256:
     def set_tuning(self, tile_bits: int, coalesce_bits: int):
         self._check(self._L.ntt256_ctx_set_tuning(self._h, tile_bits, coalesce_bits))
 
+    def set_small_transform_limit(self, max_elements: int):
+        """Calls of at most this many elements use the four-elements-per-thread kernel (0: never)."""
+        self._check(self._L.ntt256_ctx_set_small_transform_limit(self._h, max_elements))
+
+    def set_elements_per_thread(self, log2_elements: int):
+        """Force the pass kernel with 2^log2_elements (1..3) elements per thread; 0 = automatic."""
+        self._check(self._L.ntt256_ctx_set_elements_per_thread(self._h, log2_elements))
+
     def set_stream_twiddle_limit(self, max_bytes: int):
         """Largest streamed first-pass twiddle array built automatically (0: always two lookups)."""
         self._check(self._L.ntt256_ctx_set_stream_twiddle_limit(self._h, max_bytes))

@@ -29,10 +29,12 @@ constexpr int kLocBitsMax = 12;
 struct PlanKey {
   int kind;  // 0 = whole transform, 1 = four-step step 1, 2 = four-step step 2
   int log_n, log_r, log_p, rank;
-  int tile_bits = 0;  // 0 = the context's tile_bits
+  int tile_bits = 0;   // 0 = the context's tile_bits
+  int group_bits = 3;  // 3 = eight elements per thread; 2 = four (small, latency-bound transforms)
+  int coalesce = -1;   // -1 = the context's coalesce_bits
   bool operator<(const PlanKey& o) const {
-    return std::tie(kind, log_n, log_r, log_p, rank, tile_bits) <
-           std::tie(o.kind, o.log_n, o.log_r, o.log_p, o.rank, o.tile_bits);
+    return std::tie(kind, log_n, log_r, log_p, rank, tile_bits, group_bits, coalesce) <
+           std::tie(o.kind, o.log_n, o.log_r, o.log_p, o.rank, o.tile_bits, o.group_bits, o.coalesce);
   }
 };
 
@@ -53,6 +55,10 @@ struct ntt256_ctx {
   u32 w4[2][8];
   int tile_bits = 11;
   int coalesce_bits = 2;
+  U256 ninv[64];                          // Montgomery form of 2^-k, filled on first use
+  bool ninv_ok[64] = {};
+  int force_group_bits = 0;               // 0: automatic; 1..3: elements per thread = 2^k for every plan
+  long long small_limit = 1ll << 17;      // batch*n at or below this: four (half of it: two) elements per thread
   bool auto_tile = true;                  // shrink the tile for small problems so the grid fills the chip
   bool zero_copy_host = true;             // *_host entry points: first/last pass access pinned host memory directly
   std::map<int, uint4*> loc_scaled;       // log_n -> (1/n) * loc[] : folds the inverse scaling into a round twiddle
@@ -208,8 +214,9 @@ bool fourstep_args_ok(int log_n, int log_r, int log_p, int rank) {
 int get_plan(ntt256_ctx* ctx, const PlanKey& key, const Plan** out) {
   auto it = ctx->plans.find(key);
   if (it == ctx->plans.end()) {
-    PlanRequest req =
-        build_request(key, key.tile_bits ? key.tile_bits : ctx->tile_bits, ctx->coalesce_bits, ctx->max_log_n);
+    PlanRequest req = build_request(key, key.tile_bits ? key.tile_bits : ctx->tile_bits,
+                                    key.coalesce >= 0 ? key.coalesce : ctx->coalesce_bits, ctx->max_log_n);
+    req.group_bits = key.group_bits;
     Plan plan;
     bool ok = make_plan(req, &plan);
     // very small tiles with wide coalescing leave too few free tile bits: relax the run length
@@ -218,7 +225,9 @@ int get_plan(ntt256_ctx* ctx, const PlanKey& key, const Plan** out) {
       req.coalesce_bits = g;
       ok = make_plan(req, &plan, 12);
     }
-    for (int t = req.tile_bits + 1; !ok && t <= kMaxTileBits; ++t) {
+    const int max_tile = (key.group_bits == 3) ? kMaxTileBits : 11;  // 1024 / 512 threads per CTA at most
+    if (req.tile_bits > max_tile) return NTT256_ERR_PLAN;
+    for (int t = req.tile_bits + 1; !ok && t <= max_tile; ++t) {
       req.tile_bits = t;
       ok = make_plan(req, &plan, 12);
     }
@@ -239,6 +248,26 @@ struct IoSpec {  // optional out-of-place ends of a plan (device-visible pointer
   void* dst_last = nullptr;
 };
 
+// The pass kernel for 2^group_bits elements per thread.
+void launch_pass(int group_bits, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const uint4* in,
+                 uint4* out, const PassArgs& A) {
+  if (group_bits == 3)
+    ntt_pass_kernel<<<grid, threads, smem, stream>>>(in, out, A);
+  else if (group_bits == 2)
+    ntt_pass4_kernel<<<grid, threads, smem, stream>>>(in, out, A);
+  else
+    ntt_pass2_kernel<<<grid, threads, smem, stream>>>(in, out, A);
+}
+
+// (2^k)^-1 mod p in Montgomery form (a host inversion is ~10 us: computed once per k)
+const U256& inv_pow2(ntt256_ctx* ctx, int k) {
+  if (!ctx->ninv_ok[k]) {
+    ctx->ninv[k] = ctx->hf.inv(ctx->hf.to_mont(u256_small(1ull << k)));
+    ctx->ninv_ok[k] = true;
+  }
+  return ctx->ninv[k];
+}
+
 int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long batch_stride, int batch, bool inverse,
              int scale_log_n, cudaStream_t stream, const PeerSpec* peer = nullptr, const IoSpec* io = nullptr) {
   PassArgs A;
@@ -256,8 +285,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
   A.scaled_round = -1;
   const uint4* loc_scaled = nullptr;
   if (scale_log_n >= 0) {
-    U256 nm = ctx->hf.to_mont(u256_small(1ull << scale_log_n));
-    U256 ninv = ctx->hf.inv(nm);
+    const U256& ninv = inv_pow2(ctx, scale_log_n);
     to_u32(ninv, A.scale);
     if (plan.passes.back().nrounds >= 2) {
       // fold 1/n into the twiddle table of the last pass's first round (all 8 elements of that
@@ -307,7 +335,8 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
             to_u32(ctx->hf.one, G.one);
             const int Tg = G.pd.T;
             dim3 ggrid((unsigned)(1ull << G.pd.nblk_bits), 1, 1);
-            ntt_pass_kernel<<<ggrid, 1u << (Tg - 3), (size_t)32 << Tg, stream>>>((const uint4*)d_data, (uint4*)d_data, G);
+            launch_pass(plan.group_bits, ggrid, 1u << (Tg - plan.group_bits), (size_t)32 << Tg, stream,
+                        (const uint4*)d_data, (uint4*)d_data, G);
             ++ctx->launches;
             CTX_CUDA(cudaGetLastError());
             // one-off: the array may be read from other streams by later calls
@@ -327,7 +356,8 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
       A.peer_rank = peer->rank;
     }
     const int T = A.pd.T;
-    const unsigned threads = 1u << (T - 3);
+    const int GB = plan.group_bits;
+    const unsigned threads = 1u << (T - GB);
     const size_t smem = (size_t)32 << T;
     const unsigned long long nblk = 1ull << A.pd.nblk_bits;
     if (nblk > 0x7fffffffull || batch > 65535) return NTT256_ERR_ARG;
@@ -335,7 +365,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
     // first pass may read from `src_first`, last pass may write to `dst_last` (host-mapped buffers)
     const uint4* pin = (i == 0 && io && io->src_first) ? (const uint4*)io->src_first : (const uint4*)d_data;
     uint4* pout = (i + 1 == plan.passes.size() && io && io->dst_last) ? (uint4*)io->dst_last : (uint4*)d_data;
-    ntt_pass_kernel<<<grid, threads, smem, stream>>>(pin, pout, A);
+    launch_pass(GB, grid, threads, smem, stream, pin, pout, A);
     ++ctx->launches;
     CTX_CUDA(cudaGetLastError());
   }
@@ -351,8 +381,7 @@ int run_tiny(ntt256_ctx* ctx, void* d_data, int log_n, unsigned long long batch,
   std::memcpy(A.w4, ctx->w4[inverse ? 1 : 0], sizeof(A.w4));
   A.do_scale = inverse ? 1 : 0;
   if (inverse) {
-    U256 nm = ctx->hf.to_mont(u256_small(1ull << log_n));
-    to_u32(ctx->hf.inv(nm), A.scale);
+    to_u32(inv_pow2(ctx, log_n), A.scale);
   }
   A.batch = batch;
   const int threads = 128;
@@ -367,19 +396,32 @@ int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse,
   if (!ctx || !d_data || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
   CTX_CUDA(cudaSetDevice(ctx->device));
   if (log_n < 3) return run_tiny(ctx, d_data, log_n, (unsigned long long)batch, inverse, stream);
-  // Tile choice: 2^tile_bits elements per CTA is best when the grid is large; small problems
-  // get smaller tiles so that at least ~2 CTAs per SM exist (a 2^16 transform is 32 tiles of 2^11).
-  int tile = 0;
-  if (ctx->auto_tile) {
-    const long long want_ctas = 2 * 148;
-    tile = ctx->tile_bits;
-    while (tile > 8 && tile > 3 && (((long long)batch << log_n) >> tile) < want_ctas) --tile;
-    if (tile > log_n) tile = log_n;
-    if (tile == ctx->tile_bits) tile = 0;
-  }
+  // Kernel and tile choice by the number of elements E in the call (profiles/r01_small_sweep.md):
+  // large calls are throughput-bound and want eight elements per thread and 2^11-element tiles;
+  // below ~2^21 elements smaller tiles balance the 148 SMs better; below ~2^17 the call is
+  // latency-bound (few warps per SM, each a serial chain of 256-bit multiplies), so the work is cut
+  // finer: four, then two elements per thread in 2^9 / 2^8-element tiles, no coalescing constraint
+  // (the data lives in L2).
   const Plan* plan = nullptr;
   PlanKey key{0, log_n, 0, 0, 0};
-  key.tile_bits = tile;
+  if (ctx->auto_tile) {
+    const long long E = (long long)batch << log_n;
+    if (E <= ctx->small_limit / 2) {
+      key.group_bits = 1;
+      key.tile_bits = std::min(8, log_n);
+      key.coalesce = 0;
+    } else if (E <= ctx->small_limit) {
+      key.group_bits = 2;
+      key.tile_bits = std::min(9, log_n);
+      key.coalesce = 0;
+    } else if (E <= (1ll << 20)) {
+      key.tile_bits = std::min(std::min(10, ctx->tile_bits), log_n);
+    } else if (log_n < ctx->tile_bits) {
+      key.tile_bits = log_n;
+    }
+    if (key.tile_bits == ctx->tile_bits && key.group_bits == 3) key.tile_bits = 0;
+  }
+  if (ctx->force_group_bits) key.group_bits = ctx->force_group_bits;
   int rc = get_plan(ctx, key, &plan);
   if (rc) return rc;
   // batches larger than one grid dimension are issued in slices
@@ -588,7 +630,9 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
   };
   if (cudaSetDevice(device) != cudaSuccess) return fail(NTT256_ERR_CUDA);
   if (cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMaxTileBits) !=
-      cudaSuccess)
+          cudaSuccess ||
+      cudaFuncSetAttribute(ntt_pass4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess ||
+      cudaFuncSetAttribute(ntt_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess)
     return fail(NTT256_ERR_CUDA);
   rc = build_power_table(ctx, &ctx->om_hi, pow2k(ctx->hf, ctx->wN, ctx->lo_bits), ctx->hi_bits);
   if (rc) return fail(rc);
@@ -964,6 +1008,18 @@ int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes) {
   return NTT256_OK;
 }
 
+int ntt256_ctx_set_elements_per_thread(ntt256_ctx* ctx, int log2_elements) {
+  if (!ctx || log2_elements < 0 || log2_elements > 3) return NTT256_ERR_ARG;
+  ctx->force_group_bits = log2_elements;
+  return NTT256_OK;
+}
+
+int ntt256_ctx_set_small_transform_limit(ntt256_ctx* ctx, long long max_elements) {
+  if (!ctx || max_elements < 0) return NTT256_ERR_ARG;
+  ctx->small_limit = max_elements;
+  return NTT256_OK;
+}
+
 int ntt256_enable_peer_access(int device, int peer_device) {
   if (device == peer_device) return NTT256_OK;
   int can = 0;
@@ -977,8 +1033,15 @@ int ntt256_enable_peer_access(int device, int peer_device) {
   return e == cudaSuccess ? NTT256_OK : NTT256_ERR_CUDA;
 }
 
+size_t ntt256_plan_describe_ex(int log_n, int max_log_n, int tile_bits, int coalesce_bits, int group_bits, char* buf,
+                               size_t buf_len);
 size_t ntt256_plan_describe(int log_n, int max_log_n, int tile_bits, int coalesce_bits, char* buf, size_t buf_len) {
+  return ntt256_plan_describe_ex(log_n, max_log_n, tile_bits, coalesce_bits, 3, buf, buf_len);
+}
+size_t ntt256_plan_describe_ex(int log_n, int max_log_n, int tile_bits, int coalesce_bits, int group_bits, char* buf,
+                               size_t buf_len) {
   PlanRequest req;
+  req.group_bits = group_bits;
   req.log_n = log_n;
   req.max_log_n = max_log_n;
   req.tile_bits = tile_bits;

@@ -108,12 +108,58 @@ NTT_DEV unsigned long long deposit64(unsigned long long v, const int8_t* pos, in
   return r;
 }
 
-__global__ void __launch_bounds__(512, 1)
-ntt_pass_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
-  // data_in == data_out: in place (the normal case).  They differ when the first / last pass of
-  // a host-buffer transform reads / writes pinned host memory directly (zero-copy over PCIe, so the
-  // transfer overlaps the pass instead of preceding / following it).
-  extern __shared__ u32 smem[];
+// NB DIF stages on the top NB bits of the GB-bit register index, with the constant twiddles of
+// the 2^NB-point sub-transform (powers of w_8), followed -- unless this is the last round of the
+// pass -- by the round twiddle w_{2^m}^(tau_lo * v) from the table.
+template <int GB, int NB>
+NTT_DEV void round_compute(u32 (*x)[8], const PassArgs& A, const FieldParams& f, bool last, bool scaled, u32 lam0,
+                           int sb, int lowp) {
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const int bit = GB - 1 - k;
+#pragma unroll
+    for (int u = 0; u < (1 << GB); ++u) {
+      if (u & (1 << bit)) continue;
+      bfly(x[u], x[u | (1 << bit)], f);
+      const int t = (u >> (GB - NB)) & ((1 << (NB - 1 - k)) - 1);  // lower processed bits of u
+      const int e8 = t << (3 - (NB - k));                           // twiddle as a power of w_8
+      if (e8) mul_by(x[u | (1 << bit)], A.c8[e8 - 1], f);
+    }
+  }
+  if (last || NB == 0) return;
+  const int pb = sb + GB - NB;  // lowest bit butterflied in this round
+  const int m = sb + GB - lowp; // process bits from this group's top down
+  const int sh = A.loc_bits - m;
+  const u32 tl_mask = (1u << (pb - lowp)) - 1u;
+  const u32 tl0 = (lam0 >> lowp) & tl_mask;
+  const int ush = sb - lowp;    // >= 0 here (only the last round can dip below)
+  const uint4* loc_tab = scaled ? A.loc_scaled : A.loc;
+#pragma unroll
+  for (int u = 0; u < (1 << GB); ++u) {
+    // v = bit-reversed processed bits of u; tau_lo includes the group's unprocessed bits
+    const int uproc = u >> (GB - NB);
+    int v = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) v |= ((uproc >> i) & 1) << (NB - 1 - i);
+    const u32 rest = u & ((1 << (GB - NB)) - 1);
+    if (scaled || uproc != 0) {
+      const u32 tl = (tl0 | (rest << ush)) & tl_mask;
+      u32 e = (tl * (u32)v) << sh;
+      if (A.inverse) e = (0u - e);
+      e &= (1u << A.loc_bits) - 1u;
+      u32 w[8];
+      ld_table(w, loc_tab, e);
+      mul_by(x[u], w, f);
+    }
+  }
+}
+
+// One pass.  GB = log2(elements per thread): 3 is the throughput configuration (radix-8 rounds,
+// 64 data registers); 2 halves the serial work per thread and doubles the number of warps, which
+// is what small, latency-bound transforms need.
+template <int GB>
+NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs& A, u32* smem) {
+  constexpr int NE = 1 << GB;
   const PassDesc& pd = A.pd;
   const FieldParams& f = A.f;
   const int T = pd.T;
@@ -131,104 +177,62 @@ ntt_pass_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ P
   const uint4* gbase_in = data_in + 2 * base;
   uint4* gbase = data_out + 2 * base;
 
-  u32 x[8][8];
+  u32 x[NE][8];
   const bool gen = (A.tw_gen_out != nullptr);
+  const int lowp = T - d;  // lowest process bit
 
   for (int r = gen ? pd.nrounds - 1 : 0; r < pd.nrounds; ++r) {
     const int sb = pd.round_sb[r];
     const int nb = pd.round_nb[r];
-    const u32 lam0 = deposit32(tid, pd.tmap[r], T - 3);
+    const u32 lam0 = deposit32(tid, pd.tmap[r], T - GB);
     const bool first = (r == 0);
     const bool last = (r == pd.nrounds - 1);
 
-    // ---- fetch the 8 elements of this thread
+    // ---- fetch the elements of this thread
     if (gen) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < NE; ++u)
 #pragma unroll
         for (int k = 0; k < 8; ++k) x[u][k] = A.one[k];
     } else if (first) {
       const u32 g0 = deposit32(lam0, pd.in_pos, T);
-      const u32 s0 = 1u << pd.in_pos[sb], s1 = 1u << pd.in_pos[sb + 1], s2 = 1u << pd.in_pos[sb + 2];
+      u32 st[GB];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const u32 off = g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+      for (int i = 0; i < GB; ++i) st[i] = 1u << pd.in_pos[sb + i];
+#pragma unroll
+      for (int u = 0; u < NE; ++u) {
+        u32 off = g0;
+#pragma unroll
+        for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
         ld_global_256(x[u], gbase_in + 2 * (size_t)off);
       }
     } else {
       const u32 w0 = swz(lam0);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < NE; ++u) {
         const u32 w = w0 ^ swz((u32)u << sb);
 #pragma unroll
         for (int k = 0; k < 8; ++k) x[u][k] = smem[k * tile_words + w];
       }
     }
 
-    // ---- butterflies on the top nb bits of the 3-bit group
-    if (gen) {
-    } else if (nb == 3) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        bfly(x[u], x[u + 4], f);
-        if (u) mul_by(x[u + 4], A.c8[u - 1], f);
+    // ---- butterflies on the top nb bits of the group (+ round twiddle unless last)
+    if (!gen) {
+      const bool scaled = (r == A.scaled_round);
+      if (nb == 3) {
+        if constexpr (GB >= 3) round_compute<GB, 3>(x, A, f, last, scaled, lam0, sb, lowp);
+      } else if (nb == 2) {
+        if constexpr (GB >= 2) round_compute<GB, 2>(x, A, f, last, scaled, lam0, sb, lowp);
+      } else if (nb == 1) {
+        round_compute<GB, 1>(x, A, f, last, scaled, lam0, sb, lowp);
       }
-#pragma unroll
-      for (int h = 0; h < 8; h += 4)
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          bfly(x[h + u], x[h + u + 2], f);
-          if (u) mul_by(x[h + u + 2], A.c8[1], f);
-        }
-#pragma unroll
-      for (int u = 0; u < 8; u += 2) bfly(x[u], x[u + 1], f);
-    } else if (nb == 2) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        bfly(x[u], x[u + 4], f);
-        if (u & 2) mul_by(x[u + 4], A.c8[1], f);
-      }
-#pragma unroll
-      for (int h = 0; h < 8; h += 4)
-#pragma unroll
-        for (int u = 0; u < 2; ++u) bfly(x[h + u], x[h + u + 2], f);
-    } else if (nb == 1) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) bfly(x[u], x[u + 4], f);
     }
 
     if (!last) {
-      // ---- local twiddle w_{2^m}^(tau_lo * v): m = process bits from this group's top down
-      const int lowp = T - d;            // lowest process bit
-      const int pb = sb + 3 - nb;        // lowest bit butterflied in this round
-      const int m = sb + 3 - lowp;
-      const int sh = A.loc_bits - m;
-      const u32 tl_mask = (1u << (pb - lowp)) - 1u;
-      const u32 tl0 = (lam0 >> lowp) & tl_mask;
-      const int ush = sb - lowp;         // >= 0 here (only the last round can dip below)
-      const bool scaled = (r == A.scaled_round);
-      const uint4* loc_tab = scaled ? A.loc_scaled : A.loc;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        // v = bit-reversed processed bits of u; tau_lo includes the group's unprocessed bits
-        u32 v, rest;
-        if (nb == 3) { v = ((u & 4) >> 2) | (u & 2) | ((u & 1) << 2); rest = 0; }
-        else if (nb == 2) { v = ((u >> 2) & 1) | (((u >> 1) & 1) << 1); rest = u & 1; }
-        else { v = (u >> 2) & 1; rest = u & 3; }
-        if (scaled || (nb == 3 ? (u != 0) : (nb == 2 ? ((u >> 1) != 0) : ((u >> 2) != 0)))) {
-          const u32 tl = (tl0 | (rest << ush)) & tl_mask;
-          u32 e = (tl * v) << sh;
-          if (A.inverse) e = (0u - e);
-          e &= (1u << A.loc_bits) - 1u;
-          u32 w[8];
-          ld_table(w, loc_tab, e);
-          mul_by(x[u], w, f);
-        }
-      }
       // ---- exchange
       const u32 w0 = swz(lam0);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < NE; ++u) {
         const u32 w = w0 ^ swz((u32)u << sb);
 #pragma unroll
         for (int k = 0; k < 8; ++k) smem[k * tile_words + w] = x[u][k];
@@ -236,13 +240,16 @@ ntt_pass_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ P
       __syncthreads();
     } else {
       // ---- pass twiddle, scale, canonical form, store
-      const int lowp = T - d;
       const u32 g0 = deposit32(lam0, pd.out_pos, T);
-      const u32 s0 = 1u << pd.out_pos[sb], s1 = 1u << pd.out_pos[sb + 1], s2 = 1u << pd.out_pos[sb + 2];
+      u32 st[GB];
+#pragma unroll
+      for (int i = 0; i < GB; ++i) st[i] = 1u << pd.out_pos[sb + i];
       if (pd.has_tw && A.tw_stream != nullptr && !gen) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const u32 off = (u32)base_t + g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+        for (int u = 0; u < NE; ++u) {
+          u32 off = (u32)base_t + g0;
+#pragma unroll
+          for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
           u32 w[8];
           ld_table(w, A.tw_stream, off);
           mul_by(x[u], w, f);
@@ -250,17 +257,19 @@ ntt_pass_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ P
       } else if (pd.has_tw) {
         u32 jl0 = jlow_blk;
         for (int i = 0; i < lowp; ++i) jl0 += ((lam0 >> i) & 1u) * pd.wt_loc[i];
-        const u32 gw0 = (sb + 0 < lowp) ? pd.wt_loc[sb + 0] : 0u;
-        const u32 gw1 = (sb + 1 < lowp) ? pd.wt_loc[sb + 1] : 0u;
-        const u32 gw2 = (sb + 2 < lowp) ? pd.wt_loc[sb + 2] : 0u;
+        u32 gw[GB];
+#pragma unroll
+        for (int i = 0; i < GB; ++i) gw[i] = (sb + i < lowp) ? pd.wt_loc[sb + i] : 0u;
         const u32 nmask = (A.hi_bits + A.lo_bits >= 32) ? 0xffffffffu : ((1u << (A.hi_bits + A.lo_bits)) - 1u);
         const u32 lomask = (1u << A.lo_bits) - 1u;
         const bool two = pd.tw_lshift < A.lo_bits;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < NE; ++u) {
           const u32 lam = lam0 | ((u32)u << sb);
           const u32 khi = d ? (__brev(lam >> lowp) >> (32 - d)) : 0u;
-          const u32 jl = jl0 + ((u & 1) ? gw0 : 0u) + ((u & 2) ? gw1 : 0u) + ((u & 4) ? gw2 : 0u);
+          u32 jl = jl0;
+#pragma unroll
+          for (int i = 0; i < GB; ++i) jl += ((u >> i) & 1) ? gw[i] : 0u;
           u32 e = (jl * khi) << pd.tw_lshift;
           if (A.inverse) e = (0u - e);
           e &= nmask;
@@ -275,41 +284,72 @@ ntt_pass_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ P
       }
       if (pd.scale_out) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) mul_by(x[u], A.scale, f);
+        for (int u = 0; u < NE; ++u) mul_by(x[u], A.scale, f);
       }
       if (pd.is_final) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) canonicalize(x[u], f);
+        for (int u = 0; u < NE; ++u) canonicalize(x[u], f);
       }
       // a single-round pass loads and stores global memory in the same round: every thread of
       // the CTA must have loaded before any permuted store lands on another thread's input
       if (first) __syncthreads();
       if (gen) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const u32 off = (u32)base_t + g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+        for (int u = 0; u < NE; ++u) {
+          u32 off = (u32)base_t + g0;
+#pragma unroll
+          for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
           canonicalize(x[u], f);
           st_global_256(A.tw_gen_out + 2 * (size_t)off, x[u]);
         }
       } else if (A.peer_bits == 0) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const u32 off = g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+        for (int u = 0; u < NE; ++u) {
+          u32 off = g0;
+#pragma unroll
+          for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
           st_global_256(gbase + 2 * (size_t)off, x[u]);
         }
       } else {
         const u32 lowmask = (1u << A.peer_shift) - 1u;
         const u32 mine = (u32)A.peer_rank << A.peer_shift;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < NE; ++u) {
           // full local output index: block part + in-tile part
-          const u32 off = (u32)base + g0 + ((u & 1) ? s0 : 0u) + ((u & 2) ? s1 : 0u) + ((u & 4) ? s2 : 0u);
+          u32 off = (u32)base + g0;
+#pragma unroll
+          for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
           uint4* dst = reinterpret_cast<uint4*>(A.peer[off >> A.peer_shift]) + 2 * (size_t)(mine | (off & lowmask));
           st_global_256(dst, x[u]);
         }
       }
     }
   }
+}
+
+// data_in == data_out: in place (the normal case).  They differ when the first / last pass of
+// a host-buffer transform reads / writes pinned host memory directly (zero-copy over PCIe, so the
+// transfer overlaps the pass instead of preceding / following it).
+__global__ void __launch_bounds__(512, 1)
+ntt_pass_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
+  extern __shared__ u32 smem[];
+  ntt_pass_body<3>(data_in, data_out, A, smem);
+}
+
+// Four elements per thread (radix-4 rounds): twice the warps, half the serial work per thread --
+// used for small transforms, which are latency-bound with eight elements per thread.
+__global__ void __launch_bounds__(512, 1)
+ntt_pass4_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
+  extern __shared__ u32 smem[];
+  ntt_pass_body<2>(data_in, data_out, A, smem);
+}
+
+// Two elements per thread (radix-2 rounds): the lowest-latency shape, for transforms so small that
+// even the four-element kernel leaves most of the chip idle.
+__global__ void __launch_bounds__(1024, 1)
+ntt_pass2_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
+  extern __shared__ u32 smem[];
+  ntt_pass_body<1>(data_in, data_out, A, smem);
 }
 
 // Transforms of 2 or 4 points: one thread per transform, exact radix-2 DIF + bit reversal.

@@ -181,28 +181,29 @@ struct Search {
 
 int rounds_of(int d) { return d == 0 ? 1 : (d + 2) / 3; }
 
-// Fill the round schedule of a pass: a short first round (d mod 3 stages) followed by
-// radix-8 rounds; each round owns a 3-bit group of local bits and butterflies its top nb.
-void schedule_rounds(PassDesc* pd) {
+// Fill the round schedule of a pass: a short first round (d mod GB stages) followed by full
+// rounds; each round owns a GB-bit group of local bits (GB = log2 of the elements a thread
+// holds) and butterflies its top nb.
+void schedule_rounds(PassDesc* pd, int GB) {
   const int T = pd->T, d = pd->d;
   int r = 0;
   int top = T;  // next unprocessed local bit + 1
-  int first = d % 3;
+  int first = d % GB;
   if (d == 0) {
-    pd->round_sb[0] = (int8_t)std::max(T - 3, 0);
+    pd->round_sb[0] = (int8_t)std::max(T - GB, 0);
     pd->round_nb[0] = 0;
     r = 1;
   } else {
     if (first) {
-      pd->round_sb[r] = (int8_t)std::max(top - 3, 0);
+      pd->round_sb[r] = (int8_t)std::max(top - GB, 0);
       pd->round_nb[r] = (int8_t)first;
       top -= first;
       ++r;
     }
     while (top > T - d) {
-      pd->round_sb[r] = (int8_t)(top - 3);
-      pd->round_nb[r] = 3;
-      top -= 3;
+      pd->round_sb[r] = (int8_t)(top - GB);
+      pd->round_nb[r] = (int8_t)GB;
+      top -= GB;
       ++r;
     }
   }
@@ -215,7 +216,7 @@ void schedule_rounds(PassDesc* pd) {
     const int sb = pd->round_sb[rr];
     std::vector<int> avail;
     for (int b = 0; b < T; ++b)
-      if (b < sb || b >= sb + 3) avail.push_back(b);
+      if (b < sb || b >= sb + GB) avail.push_back(b);
     std::vector<int> order;
     std::vector<char> used(T, 0);
     if (rr == 0 || rr == r - 1) {
@@ -302,6 +303,8 @@ bool make_plan(const PlanRequest& req, Plan* out, int max_passes) {
   }
   if (!found) return false;
 
+  const int GB = (req.group_bits == 2 || req.group_bits == 1) ? req.group_bits : 3;
+  out->group_bits = GB;
   out->log_n = req.log_n;
   out->tile_bits = c.T;
   out->coalesce_bits = c.g;
@@ -314,6 +317,7 @@ bool make_plan(const PlanRequest& req, Plan* out, int max_passes) {
     const int d = (int)pc.proc_pos.size();
     const int T = std::max((int)pc.S.size(), 3);
     if ((int)pc.S.size() < 3) return false;  // arrays below 8 elements use the tiny kernel
+    if (d > 0 && (d + GB - 1) / GB > kMaxRounds) return false;
     pd.T = T;
     pd.d = d;
     pd.nblk_bits = c.nbits - T;
@@ -355,7 +359,7 @@ bool make_plan(const PlanRequest& req, Plan* out, int max_passes) {
     pd.jlow_const = req.jlow_const;
     pd.is_final = 0;
     pd.scale_out = 0;
-    schedule_rounds(&pd);
+    schedule_rounds(&pd, GB);
     out->passes.push_back(pd);
     lab = pc.new_label;
   }
@@ -365,7 +369,8 @@ bool make_plan(const PlanRequest& req, Plan* out, int max_passes) {
 
 std::string Plan::describe() const {
   std::ostringstream o;
-  o << "{\"log_n\": " << log_n << ", \"tile_bits\": " << tile_bits << ", \"coalesce_bits\": " << coalesce_bits
+  o << "{\"log_n\": " << log_n << ", \"tile_bits\": " << tile_bits << ", \"group_bits\": " << group_bits
+    << ", \"coalesce_bits\": " << coalesce_bits
     << ", \"passes\": [";
   for (size_t i = 0; i < passes.size(); ++i) {
     const PassDesc& p = passes[i];
@@ -391,7 +396,7 @@ std::string Plan::describe() const {
       << ", \"wt_loc\": " << arr32(p.wt_loc, p.T) << ", \"wt_blk\": " << arr32(p.wt_blk, p.nblk_bits)
       << ", \"round_sb\": " << arr8(p.round_sb, p.nrounds) << ", \"round_nb\": " << arr8(p.round_nb, p.nrounds)
       << ", \"tmap\": [";
-    for (int r = 0; r < p.nrounds; ++r) o << (r ? ", " : "") << arr8(p.tmap[r], p.T - 3);
+    for (int r = 0; r < p.nrounds; ++r) o << (r ? ", " : "") << arr8(p.tmap[r], p.T - group_bits);
     o << "]}";
   }
   o << "]}";

@@ -22,7 +22,7 @@
 namespace ntt256 {
 
 constexpr int kMaxTileBits = 12;   // 4096 elements = 128 KiB of shared memory
-constexpr int kMaxRounds = 6;
+constexpr int kMaxRounds = 12;  // T = 12 in radix-8 rounds needs 4; the two-element kernel one per stage
 constexpr int kMaxIndexBits = 40;  // log2(n * batch) the descriptors can address
 
 // One pass, as consumed by the device kernel (trivially copyable; passed by value as a
@@ -42,7 +42,7 @@ struct PassDesc {
   int8_t blk_pos[kMaxIndexBits];  // physical bit position of block-index bit i
   uint32_t wt_loc[16];            // time weight (2^b or 0) of passive local bit i
   uint32_t wt_blk[kMaxIndexBits]; // time weight of block-index bit i
-  int8_t round_sb[kMaxRounds];    // lowest local bit of the round's 3-bit group
+  int8_t round_sb[kMaxRounds];    // lowest local bit of the round's group (group_bits wide)
   int8_t round_nb[kMaxRounds];    // butterfly stages in the round (top nb bits of the group)
   int8_t tmap[kMaxRounds][16];    // local bit fed by thread-index bit i in round r
 };
@@ -51,6 +51,7 @@ struct Plan {
   int log_n = 0;
   int tile_bits = 0;   // requested T
   int coalesce_bits = 0;
+  int group_bits = 3;  // log2(elements per thread) the round schedule was made for (3, 2 or 1)
   std::vector<PassDesc> passes;
   unsigned long long id = 0;     // unique per created plan (keys per-plan device tables)
   std::string describe() const;  // JSON, for tests and DESIGN.md
@@ -75,6 +76,7 @@ struct PlanRequest {
   int time_hi = -1, time_lo = 0;  // process j_time_hi .. j_time_lo (default log_n-1 .. 0)
   uint32_t jlow_const = 0;
   int total_log_n = -1;     // length of the whole (possibly distributed) transform; default log_n
+  int group_bits = 3;       // 3: eight elements per thread (radix-8 rounds); 2: four (radix-4); 1: two (radix-2)
 };
 
 // Returns false when no plan with <= max_passes passes exists under the constraints.

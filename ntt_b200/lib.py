@@ -16,7 +16,7 @@ FIELD_BN254_FR, FIELD_BLS12_381_FR = 0, 1
 # every symbol include/ntt256.h declares
 EXPORTS = [
     "ntt256_ctx_create", "ntt256_ctx_create_named", "ntt256_ctx_destroy", "ntt256_ctx_set_tuning",
-    "ntt256_ctx_set_stream_twiddle_limit",
+    "ntt256_ctx_set_stream_twiddle_limit", "ntt256_ctx_set_small_transform_limit", "ntt256_ctx_set_elements_per_thread",
     "ntt256_forward", "ntt256_inverse", "ntt256_forward_batch", "ntt256_inverse_batch",
     "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2", "ntt256_fourstep_step1_peer", "ntt256_enable_peer_access",
     "ntt256_fourstep_inverse_step1", "ntt256_fourstep_inverse_step1_peer", "ntt256_fourstep_inverse_step2",
@@ -25,7 +25,7 @@ EXPORTS = [
     "ntt256_mgpu_synchronize", "ntt256_mgpu_destroy",
     "ntt256_vec_mul", "ntt256_to_montgomery", "ntt256_from_montgomery", "ntt256_coset_forward",
     "ntt256_coset_inverse",
-    "ntt256_plan_describe", "ntt256_plan_describe_fourstep", "ntt256_launch_count", "ntt256_strerror", "ntt256_last_cuda_error",
+    "ntt256_plan_describe", "ntt256_plan_describe_ex", "ntt256_plan_describe_fourstep", "ntt256_launch_count", "ntt256_strerror", "ntt256_last_cuda_error",
     "ntt256_version",
 ]
 
@@ -53,6 +53,8 @@ def lib() -> ctypes.CDLL:
         L.ntt256_ctx_destroy.restype = None
         L.ntt256_ctx_set_tuning.argtypes = [vp, ci, ci]
         L.ntt256_ctx_set_stream_twiddle_limit.argtypes = [vp, ctypes.c_size_t]
+        L.ntt256_ctx_set_small_transform_limit.argtypes = [vp, ctypes.c_longlong]
+        L.ntt256_ctx_set_elements_per_thread.argtypes = [vp, ci]
         for name in ("ntt256_forward", "ntt256_inverse"):
             getattr(L, name).argtypes = [vp, vp, ci, vp]
         for name in ("ntt256_forward_batch", "ntt256_inverse_batch"):
@@ -83,6 +85,8 @@ def lib() -> ctypes.CDLL:
         L.ntt256_ipc_free.argtypes = [ci, vp]
         L.ntt256_plan_describe.argtypes = [ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]
         L.ntt256_plan_describe.restype = ctypes.c_size_t
+        L.ntt256_plan_describe_ex.argtypes = [ci, ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]
+        L.ntt256_plan_describe_ex.restype = ctypes.c_size_t
         L.ntt256_plan_describe_fourstep.argtypes = [ci] * 8 + [ctypes.c_char_p, ctypes.c_size_t]
         L.ntt256_plan_describe_fourstep.restype = ctypes.c_size_t
         L.ntt256_launch_count.argtypes = [vp]
@@ -96,14 +100,15 @@ def lib() -> ctypes.CDLL:
     return _LIB
 
 
-def plan_describe(log_n: int, max_log_n: int, tile_bits: int = 11, coalesce_bits: int = 2) -> dict:
-    """Host-only: the pass plan ntt256_forward would run (JSON -> dict)."""
+def plan_describe(log_n: int, max_log_n: int, tile_bits: int = 11, coalesce_bits: int = 2, group_bits: int = 3) -> dict:
+    """Host-only: the pass plan for 2^log_n points (JSON -> dict); group_bits 3 = eight elements per
+    thread, 2 = four."""
     import json
 
     L = lib()
-    need = L.ntt256_plan_describe(log_n, max_log_n, tile_bits, coalesce_bits, None, 0)
+    need = L.ntt256_plan_describe_ex(log_n, max_log_n, tile_bits, coalesce_bits, group_bits, None, 0)
     buf = ctypes.create_string_buffer(need)
-    L.ntt256_plan_describe(log_n, max_log_n, tile_bits, coalesce_bits, buf, need)
+    L.ntt256_plan_describe_ex(log_n, max_log_n, tile_bits, coalesce_bits, group_bits, buf, need)
     return json.loads(buf.value.decode())
 
 

@@ -19,11 +19,13 @@ def _brev(v: int, bits: int) -> int:
 
 
 def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inverse: bool = False,
-             scale: int | None = None, peer: dict | None = None) -> None:
+             scale: int | None = None, peer: dict | None = None, group_bits: int = 3) -> None:
     """In-place simulation of one pass over one transform (len(data) = 2^(T + nblk_bits))."""
     T, d = pd["T"], pd["d"]
     lowp = T - d
-    nthreads = 1 << (T - 3)
+    GB = group_bits
+    NE = 1 << GB
+    nthreads = 1 << (T - GB)
     N = 1 << max_log_n
 
     def root(e: int) -> int:  # w_N^e with the kernel's inverse convention
@@ -43,8 +45,8 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
             first, last = r == 0, r == pd["nrounds"] - 1
             stores = []  # global stores happen after every thread of the CTA has loaded
             for tid in range(nthreads):
-                lam0 = _deposit(tid, pd["tmap"][r], T - 3)
-                lams = [lam0 | (u << sb) for u in range(8)]
+                lam0 = _deposit(tid, pd["tmap"][r], T - GB)
+                lams = [lam0 | (u << sb) for u in range(NE)]
                 if first:
                     x = [data[base + _deposit(l, pd["in_pos"], T)] for l in lams]
                 else:
@@ -55,40 +57,27 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
                     x[i], x[j] = (a + b) % p, (a - b) % p
 
                 w8 = lambda k: root(k * (N // 8))
-                if nb == 3:
-                    for u in range(4):
-                        bfly(u, u + 4)
-                        if u:
-                            x[u + 4] = x[u + 4] * w8(u) % p
-                    for h in (0, 4):
-                        for u in range(2):
-                            bfly(h + u, h + u + 2)
-                            if u:
-                                x[h + u + 2] = x[h + u + 2] * w8(2) % p
-                    for u in range(0, 8, 2):
-                        bfly(u, u + 1)
-                elif nb == 2:
-                    for u in range(4):
-                        bfly(u, u + 4)
-                        if u & 2:
-                            x[u + 4] = x[u + 4] * w8(2) % p
-                    for h in (0, 4):
-                        for u in range(2):
-                            bfly(h + u, h + u + 2)
-                elif nb == 1:
-                    for u in range(4):
-                        bfly(u, u + 4)
+                for k in range(nb):  # DIF stages on the top nb bits of the group, top bit first
+                    bit = GB - 1 - k
+                    for u in range(NE):
+                        if u & (1 << bit):
+                            continue
+                        bfly(u, u | (1 << bit))
+                        t = (u >> (GB - nb)) & ((1 << (nb - 1 - k)) - 1)
+                        e8 = t << (3 - (nb - k))
+                        if e8:
+                            x[u | (1 << bit)] = x[u | (1 << bit)] * w8(e8) % p
                 if not last:
-                    pb = sb + 3 - nb
-                    m = sb + 3 - lowp
+                    pb = sb + GB - nb
+                    m = sb + GB - lowp
                     sh = loc_bits - m
                     tl_mask = (1 << (pb - lowp)) - 1
                     tl0 = (lam0 >> lowp) & tl_mask
                     ush = sb - lowp
-                    for u in range(8):
-                        uproc = u >> (3 - nb)
+                    for u in range(NE):
+                        uproc = u >> (GB - nb)
                         v = _brev(uproc, nb)
-                        rest = u & ((1 << (3 - nb)) - 1)
+                        rest = u & ((1 << (GB - nb)) - 1)
                         fold = scale is not None and pd.get("scaled_round", -1) == r
                         if uproc != 0 or fold:
                             tl = (tl0 | (rest << ush)) & tl_mask
@@ -96,20 +85,20 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
                             x[u] = x[u] * root(e * (N >> loc_bits)) % p
                             if fold:
                                 x[u] = x[u] * scale % p
-                    for u in range(8):
+                    for u in range(NE):
                         tile[lams[u]] = x[u]
                 else:
                     if pd["has_tw"]:
                         jl0 = jlow_blk + sum(((lam0 >> i) & 1) * pd["wt_loc"][i] for i in range(lowp))
-                        gw = [pd["wt_loc"][sb + i] if sb + i < lowp else 0 for i in range(3)]
-                        for u in range(8):
+                        gw = [pd["wt_loc"][sb + i] if sb + i < lowp else 0 for i in range(GB)]
+                        for u in range(NE):
                             khi = _brev(lams[u] >> lowp, d) if d else 0
-                            jl = jl0 + sum(gw[i] for i in range(3) if (u >> i) & 1)
+                            jl = jl0 + sum(gw[i] for i in range(GB) if (u >> i) & 1)
                             e = ((jl * khi) << pd["tw_lshift"]) & (N - 1)
                             x[u] = x[u] * root(e) % p
                     if scale is not None and pd.get("scale_out"):
                         x = [v * scale % p for v in x]
-                    for u in range(8):
+                    for u in range(NE):
                         stores.append((base + _deposit(lams[u], pd["out_pos"], T), x[u]))
             for pos, val in stores:
                 if peer is None:
@@ -134,5 +123,5 @@ def run_plan(data: list[int], plan: dict, p: int, g: int, max_log_n: int, invers
                 pd["scaled_round"] = 0  # 1/n folded into the first round's twiddle table
             else:
                 pd["scale_out"] = 1
-        run_pass(out, pd, p, w_max, max_log_n, inverse, scale)
+        run_pass(out, pd, p, w_max, max_log_n, inverse, scale, group_bits=plan.get("group_bits", 3))
     return out

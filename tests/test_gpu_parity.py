@@ -630,3 +630,61 @@ def test_2p26_properties(torch_cuda):
     torch.cuda.synchronize()
     assert torch.equal(d, src)
     ctx.close()
+
+
+# --------------------------------------------------------------------------- small-transform kernel
+@pytest.mark.parametrize("field", ["bn254_fr", "ref29"])
+def test_small_transform_kernel_matches_throughput_kernel_and_oracle(torch_cuda, field):
+    """Calls of <= 2^16 / 2^17 elements run on ntt_pass2_kernel / ntt_pass4_kernel (two / four elements
+    per thread); the same calls with that path disabled run on ntt_pass_kernel.  All must give the
+    oracle's bits."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    p, g = FIELDS[field]
+    small = Ntt256(field, max_log_n=18)
+    big = Ntt256(field, max_log_n=18)
+    big.set_small_transform_limit(0)
+    try:
+        for log_n, batch in ((4, 1), (5, 3), (7, 1), (9, 5), (11, 1), (12, 2), (13, 1), (14, 16), (16, 1), (16, 2), (13, 16), (17, 1),
+                             (18, 1), (10, 256)):
+            n = 1 << log_n
+            x = co.splitmix_elements(n * batch, p, 0x5A11 + log_n)
+            want = np.concatenate([co.ntt(x[b * n:(b + 1) * n], p, g, threads=4) for b in range(batch)])
+            for ctx in (small, big):
+                before = ctx.launch_count
+                got = _gpu_forward(torch_cuda, ctx, x, log_n, batch)
+                assert np.array_equal(got, want), (log_n, batch, ctx is small)
+                assert np.array_equal(_gpu_forward(torch_cuda, ctx, got, log_n, batch, inverse=True), x)
+                assert ctx.launch_count > before
+    finally:
+        small.close()
+        big.close()
+
+
+def test_transform_is_capturable_in_a_cuda_graph(torch_cuda, ctxs):
+    """After one warm-up call (lazy tables are built outside capture) a forward+inverse pair can be
+    captured in a CUDA graph and replayed: launch-bound callers of small transforms replay graphs."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 20)
+    log_n, batch = 12, 3
+    n = 1 << log_n
+    x = co.splitmix_elements(n * batch, p, 0x6A4)
+    want = np.concatenate([co.ntt(x[b * n:(b + 1) * n], p, g, threads=4) for b in range(batch)])
+    d = torch.from_numpy(np.array(x, dtype=np.uint32, copy=True).view(np.int32)).cuda()
+    ctx.forward(d, log_n, batch)
+    ctx.inverse(d, log_n, batch)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ctx.forward(d, log_n, batch)
+    for _ in range(3):  # forward three times = replay thrice; undo two of them
+        graph.replay()
+    ctx.inverse(d, log_n, batch)
+    ctx.inverse(d, log_n, batch)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 8), want)

@@ -25,7 +25,8 @@ def _check_plan_invariants(plan, L, T, g):
         for r in range(pd["nrounds"]):
             sb = pd["round_sb"][r]
             tm = pd["tmap"][r]
-            assert sorted(tm + [sb, sb + 1, sb + 2]) == list(range(pd["T"]))
+            gb = plan.get("group_bits", 3)
+            assert sorted(tm + [sb + i for i in range(gb)]) == list(range(pd["T"]))
     assert total == L
     assert plan["passes"][-1]["is_final"] == 1 and plan["passes"][-1]["has_tw"] == 0
 
@@ -37,6 +38,24 @@ def test_plan_executes_to_the_oracle(built, L, T, g):
     assert "error" not in plan
     _check_plan_invariants(plan, L, T, g)
     rng = random.Random(L * 100 + T)
+    for F in (po.BN254_FR, po.REF29):
+        x = [rng.randrange(F.p) for _ in range(1 << L)]
+        want = po.ntt_ref(x, F)
+        assert plan_sim.run_plan(x, plan, F.p, F.g, 14) == want
+        assert plan_sim.run_plan(want, plan, F.p, F.g, 14, inverse=True) == x
+
+
+@pytest.mark.parametrize("L,T,g", [(4, 4, 0), (5, 5, 0), (7, 7, 0), (8, 8, 0), (10, 10, 0), (11, 11, 0), (12, 11, 0),
+                                   (13, 7, 0), (12, 6, 1), (13, 11, 2), (9, 4, 0)])
+@pytest.mark.parametrize("gb", [2, 1])
+def test_small_kernel_plans_execute_to_the_oracle(built, L, T, g, gb):
+    """group_bits = 2 / 1: the round schedules of ntt_pass4_kernel / ntt_pass2_kernel (small,
+    latency-bound transforms)."""
+    plan = plan_describe(L, 14, T, g, group_bits=gb)
+    assert "error" not in plan
+    assert plan["group_bits"] == gb
+    _check_plan_invariants(plan, L, T, g)
+    rng = random.Random(L * 100 + T + 7)
     for F in (po.BN254_FR, po.REF29):
         x = [rng.randrange(F.p) for _ in range(1 << L)]
         want = po.ntt_ref(x, F)
