@@ -69,7 +69,8 @@ int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits);
  * exponent range: either two table lookups and one extra product per element, or one coalesced
  * read from an n-entry array laid out like the pass's output (32*n bytes per (size, direction),
  * built on first use, kept in the context).  Arrays up to max_bytes are built automatically
- * (default 1 GiB, i.e. n <= 2^25); 0 selects the two-lookup path always. */
+ * (default: 1/16 of the device's memory, i.e. every n <= 2^28 on a 180 GB B200; when the
+ * allocation fails the two-lookup path is used); 0 selects the two-lookup path always. */
 int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes);
 /* Calls with batch * 2^log_n <= max_elements (default 2^17) are latency-bound and run on the
  * four-elements-per-thread kernel, those of at most half that on the two-elements-per-thread

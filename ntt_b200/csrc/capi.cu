@@ -64,7 +64,8 @@ struct ntt256_ctx {
   std::map<int, uint4*> loc_scaled;       // log_n -> (1/n) * loc[] : folds the inverse scaling into a round twiddle
   // streamed pass-twiddle arrays, keyed by (plan id, pass index, direction)
   std::map<std::tuple<unsigned long long, int, int>, uint4*> tw_streams;
-  size_t tw_stream_limit = (size_t)1 << 30;   // largest array built automatically (bytes); 0 = never
+  size_t tw_stream_limit = (size_t)1 << 30;   // largest array built automatically (bytes); 0 = never;
+                                              // set to 1/16 of the device's memory at creation
   unsigned long long next_plan_id = 1;
   struct CosetTables {
     U256 shift;
@@ -629,6 +630,12 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
     return code;
   };
   if (cudaSetDevice(device) != cudaSuccess) return fail(NTT256_ERR_CUDA);
+  {
+    // a streamed first-pass twiddle array is as large as the transform itself; allow each one 1/16
+    // of the device (11 GiB on a 180 GB B200: every size up to 2^28)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) ctx->tw_stream_limit = total_b / 16;
+  }
   if (cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMaxTileBits) !=
           cudaSuccess ||
       cudaFuncSetAttribute(ntt_pass4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess ||
