@@ -18,7 +18,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -40,12 +39,15 @@ def _peaks():
 
 
 class ClockSampler:
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """SM clock and throttle reasons through NVML, sampled while the timed region's kernels run.
+
+    No sampling thread: a Python thread polling NVML competes with the launching thread for the GIL
+    and the driver, which costs a multi-GPU step of 0.5 ms (three launches and a barrier) ~25 %.
+    Instead the launching thread samples after it has enqueued every timed step, while the GPU is
+    still working through them (`poll_until(end_event)`)."""
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._thread = None
         try:
             import pynvml
 
@@ -56,35 +58,32 @@ class ClockSampler:
         except Exception:
             self._nv = None
 
-    def _run(self):
+    def sample(self):
         nv = self._nv
+        if nv is None:
+            return
         names = {
             "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
             "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
             "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
             "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
         }
-        while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception:
-                pass
-            time.sleep(0.004)
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
 
-    def __enter__(self):
-        if self._nv:
-            self._thread = threading.Thread(target=self._run, daemon=True)
-            self._thread.start()
-        return self
-
-    def __exit__(self, *a):
-        self._stop.set()
-        if self._thread:
-            self._thread.join()
+    def poll_until(self, end_event, interval_s: float = 0.002):
+        """Sample until `end_event` (recorded after the last timed step) has completed."""
+        self.sample()  # at least one, taken right after the last launch was enqueued
+        while not end_event.query():
+            time.sleep(interval_s)
+            if not end_event.query():
+                self.sample()
 
     def summary(self):
         s = sorted(self.samples)
@@ -200,7 +199,8 @@ def run_ours(args):
     else:
         from ntt_b200.dist import FourStep
 
-        fs = FourStep(ctx, LOG_N, world, rank, fused=not args.no_fused, log_r=(args.log_r or None))
+        fs = FourStep(ctx, LOG_N, world, rank, fused=not args.no_fused, log_r=(args.log_r or None),
+                      barrier=args.barrier)
         x_shard = c_oracle.splitmix_elements(n // world, p, 0x4E5454 + 100 + rank)
         fs.load_shard(torch.from_numpy(x_shard.view(np.int32)).cuda())
 
@@ -226,13 +226,14 @@ def run_ours(args):
         dist.barrier()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(args.steps):
-            step()
-        e1.record(stream)
-        torch.cuda.synchronize()
+    clk = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    clk.poll_until(e1)  # the GPU is still inside the timed region: the host ran ahead of it
+    torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     if dist:
         t = torch.tensor([ms_total], device="cuda")
@@ -315,7 +316,7 @@ def run_ours(args):
         "dtype": "u32x8 (256-bit modular integer)", "data": "synthetic",
         "config": {"workload": f"2^{LOG_N}-point forward NTT, {FIELD} (8x u32 limbs), in place, natural order in/out"
                                + ("" if world == 1 else f", four-step over {world} GPUs, exchange = "
-                                  + ("NCCL all-to-all" if args.no_fused else "peer stores fused into the butterfly kernel (NVLink)")),
+                                  + ("NCCL all-to-all" if args.no_fused else "peer stores fused into the butterfly kernel (NVLink), " + args.barrier + " barrier")),
                    "field": FIELD, "log_n": LOG_N, "passes_per_step": passes,
                    "l2_policy": "input 512 MiB > 126 MB L2, no flush needed",
                    "binding_roofline": "int32-multiply pipe (see roofline_int); HBM is ~6x off"},
@@ -354,6 +355,8 @@ def main():
     ap.add_argument("--coalesce-bits", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of fused peer stores")
+    ap.add_argument("--barrier", choices=("flags", "nccl"), default="flags",
+                    help="multi-GPU fused path: peer-memory flag barrier (default) or a one-element NCCL all-reduce")
     ap.add_argument("--log-r", type=int, default=0, help="multi-GPU: rows = 2^log_r of the four-step view (0: automatic)")
     ap.add_argument("--field", default="bn254_fr", choices=["bn254_fr", "bls12_381_fr"])
     ap.add_argument("--log-n", type=int, default=24, help="transform size (default: the BASELINE metric's 2^24)")

@@ -172,6 +172,18 @@ int ntt256_ipc_alloc(int device, size_t bytes, void** d_ptr, unsigned char handl
 int ntt256_ipc_open(int device, const unsigned char handle[64], void** d_ptr);
 int ntt256_ipc_close(int device, void* d_ptr);
 int ntt256_ipc_free(int device, void* d_ptr);
+
+/* Stream-ordered barrier between the ranks of a fused four-step transform, through peer memory
+ * (no host involvement, no NCCL launch): flag_bufs[r] is rank r's flag buffer as mapped in THIS
+ * process (an ntt256_ipc_alloc'ed buffer of >= 4 KiB, zero-filled from byte 256 on, never written
+ * by anything else; flag_bufs[rank] is the local one).  One tiny kernel on `stream` publishes
+ * `epoch` in every peer's buffer (after a system-scope fence, so the peer stores of the kernels
+ * before it on the stream are visible first) and waits until every peer has published an epoch
+ * >= `epoch` here.  Epochs must increase by one per call, identically on every rank.  A peer that
+ * does not arrive within ~5 s traps the kernel (the stream then reports an error) instead of
+ * hanging the GPU.  nranks <= 8. */
+int ntt256_peer_barrier(int device, void* const* flag_bufs, int nranks, int rank, unsigned long long epoch,
+                        ntt256_stream stream);
 /* Lets kernels running on `device` store into memory of `peer_device` (NVLink peer access);
  * needed once per peer before ntt256_fourstep_step1_peer.  Already-enabled is not an error. */
 int ntt256_enable_peer_access(int device, int peer_device);

@@ -1027,6 +1027,49 @@ int ntt256_ctx_set_small_transform_limit(ntt256_ctx* ctx, long long max_elements
   return NTT256_OK;
 }
 
+namespace {
+struct PeerBarrierArgs {
+  unsigned long long flags[8];  // every rank's flag buffer, as mapped in this process
+  unsigned long long epoch;
+  int nranks, rank;
+};
+
+// Thread r: publish `epoch` in rank r's slot [rank], then wait for rank r's epoch in the local slot [r].
+__global__ void peer_barrier_kernel(const __grid_constant__ PeerBarrierArgs A) {
+  const int r = threadIdx.x;
+  if (r >= A.nranks) return;
+  constexpr int kSlotBase = 256 / 8;  // flags start at byte 256 (the first words carry the IPC check stamp)
+  __threadfence_system();
+  volatile unsigned long long* theirs = (volatile unsigned long long*)A.flags[r] + kSlotBase + A.rank;
+  *theirs = A.epoch;
+  volatile unsigned long long* mine = (volatile unsigned long long*)A.flags[A.rank] + kSlotBase + r;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (*mine < A.epoch) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 5000000000ull) __trap();  // a peer died: fail loudly rather than hang the GPU
+  }
+  __threadfence_system();
+}
+}  // namespace
+
+int ntt256_peer_barrier(int device, void* const* flag_bufs, int nranks, int rank, unsigned long long epoch,
+                        ntt256_stream stream) {
+  if (!flag_bufs || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks || epoch == 0) return NTT256_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return NTT256_ERR_CUDA;
+  PeerBarrierArgs A;
+  std::memset(&A, 0, sizeof(A));
+  for (int r = 0; r < nranks; ++r) {
+    if (!flag_bufs[r]) return NTT256_ERR_ARG;
+    A.flags[r] = (unsigned long long)flag_bufs[r];
+  }
+  A.epoch = epoch;
+  A.nranks = nranks;
+  A.rank = rank;
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(A);
+  return cudaGetLastError() == cudaSuccess ? NTT256_OK : NTT256_ERR_CUDA;
+}
+
 int ntt256_enable_peer_access(int device, int peer_device) {
   if (device == peer_device) return NTT256_OK;
   int can = 0;

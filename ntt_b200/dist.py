@@ -88,13 +88,19 @@ class FourStep:
     """
 
     def __init__(self, ctx, log_n: int, world: int, rank: int, log_r: int | None = None, group=None,
-                 fused: bool = False):
+                 fused: bool = False, barrier: str = "flags"):
         self.ctx, self.log_n, self.world, self.rank, self.group = ctx, log_n, world, rank, group
         self.log_p = _log2(world)
         self.log_r = default_log_r(log_n) if log_r is None else log_r
         if self.log_r < self.log_p or log_n - self.log_r < self.log_p:
             raise ValueError("both R and C must be multiples of the world size")
         self.fused = bool(fused) and world > 1
+        # how the fused path separates step 1 (peer stores) from step 2: "flags" = the library's
+        # peer-memory barrier kernel (ntt256_peer_barrier), "nccl" = a one-element all-reduce
+        if barrier not in ("flags", "nccl"):
+            raise ValueError("barrier must be 'flags' or 'nccl'")
+        self.barrier = barrier
+        self._epoch = 0
         self.a = None
         self.b = None
         self._peers = None  # [(ptrs of every rank's buffer a), (ptrs of every rank's buffer b)]
@@ -109,6 +115,9 @@ class FourStep:
             self._dev = shard.device.index
             self.a, self._ha = self._ipc_buffer(nbytes, 0)
             self.b, self._hb = self._ipc_buffer(nbytes, 1)
+            self._f, self._hf = self._ipc_buffer(4096, 2)
+            self._f[1:].zero_()
+            torch.cuda.synchronize()
             self._exchange_handles()
             self.a.copy_(shard.contiguous().view(-1).view(torch.int32))
             torch.cuda.synchronize()
@@ -146,7 +155,7 @@ class FourStep:
         raw = _Raw()
         t = torch.as_tensor(raw, device=torch.device("cuda", self._dev))
         assert t.data_ptr() == ptr.value
-        t[0] = self._MAGIC + 2 * self.rank + which
+        t[0] = self._MAGIC + 4 * self.rank + which
         torch.cuda.synchronize()
         self._keep.append(raw)
         return t, handle.raw
@@ -159,12 +168,12 @@ class FourStep:
         from .lib import Ntt256Error, lib
 
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, (self._ha, self._hb), group=self.group)
-        ptrs = [[], []]
+        dist.all_gather_object(everyone, (self._ha, self._hb, self._hf), group=self.group)
+        ptrs = [[], [], []]
         for r, pair in enumerate(everyone):
             for k, h in enumerate(pair):
                 if r == self.rank:
-                    ptrs[k].append((self.a if k == 0 else self.b).data_ptr())
+                    ptrs[k].append((self.a, self.b, self._f)[k].data_ptr())
                 else:
                     p = ctypes.c_void_p()
                     rc = lib().ntt256_ipc_open(self._dev, h, ctypes.byref(p))
@@ -172,14 +181,35 @@ class FourStep:
                         raise Ntt256Error(rc, f"ipc_open of rank {r}'s buffer")
                     self._opened.append(p.value)
                     ptrs[k].append(p.value)
-                    if self._peek(p.value) != self._MAGIC + 2 * r + k:
+                    if self._peek(p.value) != self._MAGIC + 4 * r + k:
                         raise RuntimeError(f"IPC mapping of rank {r}'s buffer {k} does not start at the buffer")
         import torch
 
-        self._peers = ptrs
+        self._peers = ptrs[:2]
+        self._flag_ptrs = (ctypes.c_void_p * self.world)(*ptrs[2])
         self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", self._dev))
         self._cur = 0  # which buffer holds the input
         dist.barrier(group=self.group)
+
+    def _step_barrier(self):
+        """Every rank's step-1 kernel (and its peer stores) is complete before any rank's step 2
+        starts; stream-ordered, the host does not block."""
+        if self.barrier == "flags":
+            import torch
+
+            from .lib import Ntt256Error, lib
+
+            self._epoch += 1
+            rc = lib().ntt256_peer_barrier(self._dev, self._flag_ptrs, self.world, self.rank, self._epoch,
+                                           torch.cuda.current_stream().cuda_stream)
+            if rc:
+                raise Ntt256Error(rc, "peer_barrier")
+        else:
+            import torch.distributed as dist
+
+            # a 1-element all-reduce completes on a rank only after every rank's NCCL kernel has
+            # started, i.e. after every rank's step-1 kernel has finished
+            dist.all_reduce(self._flag, group=self.group)
 
     def _peek(self, ptr):
         import torch
@@ -208,7 +238,7 @@ class FourStep:
             for p in self._owned:
                 lib().ntt256_ipc_free(self._dev, p)
             self._opened, self._owned, self._peers = [], [], None
-            self.a = self.b = None
+            self.a = self.b = self._f = None
 
     def inverse(self):
         """Distributed inverse (with 1/n): consumes shards in the forward's OUTPUT layout and
@@ -220,7 +250,7 @@ class FourStep:
             src, dst = (self.a, self.b) if self._cur == 0 else (self.b, self.a)
             ctx.fourstep_inverse_step1(src, self.log_n, self.log_r, self.log_p, self.rank,
                                        peer_ptrs=self._peers[1 - self._cur])
-            dist.all_reduce(self._flag, group=self.group)
+            self._step_barrier()
             ctx.fourstep_inverse_step2(dst, self.log_n, self.log_r, self.log_p, self.rank)
             self._cur = 1 - self._cur
             return dst
@@ -240,10 +270,7 @@ class FourStep:
         if self.fused:
             src, dst = (self.a, self.b) if self._cur == 0 else (self.b, self.a)
             ctx.fourstep_step1_peer(src, self._peers[1 - self._cur], self.log_n, self.log_r, self.log_p, self.rank)
-            # stream-ordered barrier without blocking the host: a 1-element all-reduce completes on a
-            # rank only after every rank's NCCL kernel has started, i.e. after every rank's step-1
-            # kernel (and its peer stores) has finished
-            dist.all_reduce(self._flag, group=self.group)
+            self._step_barrier()
             ctx.fourstep_step2(dst, self.log_n, self.log_r, self.log_p, self.rank)
             self._cur = 1 - self._cur
             return dst

@@ -21,11 +21,11 @@ torch.cuda.set_device(lr_)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
 p, g = FIELDS["bls12_381_fr"]
 ctx = Ntt256("bls12_381_fr", max_log_n=22, device=lr_)
-for fused in (False, True):
+for fused, barrier in ((False, "nccl"), (True, "nccl"), (True, "flags")):
   for log_n in (14, 20):
     x = co.splitmix_elements(1 << log_n, p, 99 + log_n)          # same on every rank
     shard = nd.scatter_input(x, log_n, world)[rank]
-    fs = nd.FourStep(ctx, log_n, world, rank, fused=fused).load_shard(torch.from_numpy(shard.view(np.int32)).cuda().view(-1))
+    fs = nd.FourStep(ctx, log_n, world, rank, fused=fused, barrier=barrier).load_shard(torch.from_numpy(shard.view(np.int32)).cuda().view(-1))
     out = fs.forward().clone()
     torch.cuda.synchronize()
     gathered = [torch.empty_like(out) for _ in range(world)]
@@ -41,6 +41,13 @@ for fused in (False, True):
     out2 = fs.forward().clone()
     torch.cuda.synchronize()
     assert torch.equal(out2, out)
+    # back-to-back transforms without host synchronisation: forward/inverse pairs must keep
+    # restoring the shard (exercises the barrier's epoch counting and the ping-pong buffers)
+    for _ in range(6):
+        fs.inverse(); fs.forward()
+    out3 = fs.inverse().clone()
+    torch.cuda.synchronize()
+    assert np.array_equal(out3.cpu().numpy().view(np.uint32).reshape(-1, 8), shard)
     dist.barrier()
     if fused:
         fs.close()
