@@ -233,13 +233,13 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
+    clk = ClockSampler(local_rank)  # NVML init takes a different time on every rank: before the barrier
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count
     torch.cuda.synchronize()
     if dist:
-        dist.barrier()
-    launches0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clk = ClockSampler(local_rank)
-    torch.cuda.synchronize()
+        dist.barrier()  # all ranks enter the timed region together (a late rank would be waited for
+        torch.cuda.synchronize()  # inside the first step's barrier and inflate everyone's time)
     e0.record(stream)
     for _ in range(args.steps):
         step()

@@ -688,3 +688,24 @@ def test_transform_is_capturable_in_a_cuda_graph(torch_cuda, ctxs):
     ctx.inverse(d, log_n, batch)
     torch.cuda.synchronize()
     assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 8), want)
+
+
+def test_u64_limb_view_is_the_same_bytes(torch_cuda, ctxs):
+    """prover stacks hold field elements as 4 x u64 little-endian limbs; on a
+    little-endian host that is byte-for-byte the 8 x u32 layout, so the same buffer goes in."""
+    from ntt_b200.api import FIELDS
+    from oracle import py_oracle as po
+
+    torch = torch_cuda
+    p, g = FIELDS["bls12_381_fr"]
+    ctx = ctxs("bls12_381_fr", 20)
+    log_n = 9
+    rng = np.random.default_rng(11)
+    vals = [int.from_bytes(rng.bytes(32), "little") % p for _ in range(1 << log_n)]
+    x64 = np.array([[(v >> (64 * k)) & (2**64 - 1) for k in range(4)] for v in vals], dtype=np.uint64)
+    d = torch.from_numpy(x64.view(np.int64)).cuda()          # int64[n, 4] on the device
+    ctx.forward(d, log_n)
+    torch.cuda.synchronize()
+    got64 = d.cpu().numpy().view(np.uint64)
+    got = [sum(int(got64[i, k]) << (64 * k) for k in range(4)) for i in range(1 << log_n)]
+    assert got == po.ntt_ref(vals, po.BLS12_381_FR)
