@@ -236,6 +236,7 @@ def run_ours(args):
     clk = ClockSampler(local_rank)  # NVML init takes a different time on every rank: before the barrier
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.launch_count
+    barriers0 = fs._epoch if fs is not None else 0  # peer-barrier kernels (fused multi-GPU path)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()  # all ranks enter the timed region together (a late rank would be waited for
@@ -252,6 +253,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     launches = ctx.launch_count - launches0
+    barrier_launches = (fs._epoch if fs is not None else 0) - barriers0
     ms_step = ms_total / args.steps
     value = n / (ms_step / 1e3)
 
@@ -342,7 +344,7 @@ def run_ours(args):
                          "carry_chain_peak": 9.2, "frac_of_carry_chain_peak": int_achieved / 9.2e12,
                          "note": "256-bit products need carry-predicate IMAD.WIDE forms, which run at half rate on "
                                  "B200 (9.2 T/s): profiles/r01_microbench_notes.md"},
-        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches + barrier_launches),
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = max(1, os.cpu_count() or 1)
