@@ -73,3 +73,25 @@ def test_production_plans_exist_and_are_short(built, L):
     # the headline configuration: 2^24 in three in-place passes with 128-byte runs
     if L == 24:
         assert len(plan_describe(24, 24, 12, 2)["passes"]) == 3
+
+
+def test_every_small_configuration_executes_to_the_oracle(built):
+    """Sweep of (log_n, elements per thread, tile bits, coalescing bits): every plan the planner
+    returns must transform correctly (forward and inverse) in the kernel model; requests it cannot
+    satisfy must say so (the library then relaxes them, capi.cu get_plan)."""
+    F = po.REF29
+    ok = noplan = 0
+    for L in range(3, 10):
+        x = [random.Random(L).randrange(F.p) for _ in range(1 << L)]
+        want = po.ntt_ref(x, F)
+        for gb in (1, 2, 3):
+            for T in range(3, (12 if gb == 3 else 11) + 1):
+                for g in range(0, min(T, 4) + 1):
+                    plan = plan_describe(L, 14, T, g, group_bits=gb)
+                    if "error" in plan:
+                        noplan += 1
+                        continue
+                    assert plan_sim.run_plan(x, plan, F.p, F.g, 14) == want, (L, gb, T, g)
+                    assert plan_sim.run_plan(want, plan, F.p, F.g, 14, inverse=True) == x, (L, gb, T, g)
+                    ok += 1
+    assert ok > 700 and noplan < ok // 8
