@@ -175,6 +175,52 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_gpu(args):
+    """--impl reference-gpu: the reference's OWN GPU implementation on this box.  oracle/_ref/ref_bignum
+    is /root/reference/src/big-num.cu compiled unmodified for sm_100a (oracle/Makefile, target ref256):
+    its main() runs NTT_GPU_Naive and NTT_GZKP (CGBN, 8 threads per 256-bit element) on x[i] = i for
+    2^5..2^24 points, checks each against its CPU NTT and prints kernel-only cudaEvent times -- the
+    same timing convention as this bench's `value`.  The 256-bit arithmetic does not depend on the
+    modulus, so its 2^24 line is comparable with the BN254 workload."""
+    import re
+    import subprocess
+
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_bignum")
+    if not os.path.exists(exe):
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref/ref_bignum not built (make -C oracle ref256 needs /root/reference)"}))
+        return
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900).stdout
+    rows, cur = [], {}
+    for ln in out.splitlines():
+        m = re.match(r"(cpu|naive|GZKP): ([0-9.]+)ms", ln.strip())
+        if not m:
+            cur.setdefault("mismatch_lines", 0)
+            cur["mismatch_lines"] += 1
+            continue
+        cur[m.group(1)] = float(m.group(2))
+        if m.group(1) == "GZKP":
+            rows.append(cur)
+            cur = {}
+    for i, r in enumerate(rows):
+        r["log_n"] = 5 + i  # the program sweeps kk = 5..24 (big-num.cu:370)
+    last = rows[-1]
+    best_ms = min(last["naive"], last["GZKP"])
+    n = 1 << last["log_n"]
+    line = {
+        "impl": "reference-gpu", "metric": f"ntt256_elements_per_s_2^{last['log_n']}", "value": n / (best_ms / 1e3),
+        "unit": UNIT, "n_gpus": 1, "ms_per_step": best_ms, "higher_is_better": True, "dtype": "u32x8 (CGBN, 8 threads per element)",
+        "data": "x[i] = i (the program's own input)",
+        "config": {"workload": f"2^{last['log_n']}-point forward NTT, 256-bit containers, p = 469762049, unmodified "
+                               "reference program (NTT_GPU_Naive / NTT_GZKP, kernel-only cudaEvent time as it prints it)"},
+        "reference_ms": {"naive": last["naive"], "gzkp": last["GZKP"], "cpu_int64_single_thread": last["cpu"]},
+        "self_check_mismatch_lines": sum(r.get("mismatch_lines", 0) for r in rows),
+        "all_sizes": [{k: r[k] for k in ("log_n", "cpu", "naive", "GZKP")} for r in rows],
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -364,7 +410,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--coalesce-bits", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -382,6 +428,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_ours(args)
 

@@ -128,3 +128,30 @@ def splitmix_elements(n: int, p: int, seed: int) -> np.ndarray:
 
 def max_threads() -> int:
     return lib().oracle_max_threads()
+
+
+_REF256 = None
+
+
+def ref256_lib():
+    """The reference's own 256-bit GPU drivers (NTT_GPU_Naive / NTT_GZKP of big-num.cu, compiled
+    unmodified: oracle/ref256_harness.cu) or None when oracle/_ref/libref256.so is absent.  Needs a GPU."""
+    global _REF256
+    if _REF256 is None:
+        path = os.path.join(_HERE, "_ref", "libref256.so")
+        if not os.path.exists(path):
+            return None
+        R = ctypes.CDLL(path)
+        u32p = ctypes.POINTER(ctypes.c_uint32)
+        R.ref256_ntt.argtypes = [u32p, ctypes.c_uint, u32p, u32p, ctypes.c_int]
+        _REF256 = R
+    return _REF256
+
+
+def ref256_ntt(x: np.ndarray, log_n: int, p: int, g: int, driver: int = 1) -> np.ndarray:
+    """Forward NTT of uint32[n, 8] through the reference driver (0 = NTT_GPU_Naive, 1 = NTT_GZKP)."""
+    a = np.array(x, dtype=np.uint32, copy=True)
+    rc = ref256_lib().ref256_ntt(_p(a), log_n, _p(limbs(p)), _p(limbs(g)), driver)
+    if rc:
+        raise RuntimeError(f"reference driver failed: CUDA error {rc}")
+    return a

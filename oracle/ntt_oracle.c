@@ -14,8 +14,10 @@
  * all values written back are canonical, so results equal the reference's `%` arithmetic.
  *
  * Parity status: pinned for p = 469762049, g = 3 (the reference's only field) by
- * tests/golden/ref_i64_kat.json and oracle/_ref; BN254 Fr / BLS12-381 Fr are unpinned by the
- * reference itself (it never runs them) and anchored by tests/golden/anchors.json + py_oracle.py.
+ * tests/golden/ref_i64_kat.json and oracle/_ref; BN254 Fr / BLS12-381 Fr are pinned by the outputs
+ * of the reference's own GPU drivers run on those fields (tests/golden/ref256_gpu_kat.json, made by
+ * scripts/gen_golden_ref256.py from oracle/_ref/libref256.so) and anchored by
+ * tests/golden/anchors.json + py_oracle.py.
  *
  * Build: gcc -O3 -march=native -fopenmp -shared -fPIC -o liboracle.so ntt_oracle.c
  */

@@ -10,10 +10,11 @@ Parity status
   /root/reference/src/big-num.cu:9-10): PINNED -- reproduces the known-answer vectors
   generated from the reference's own code (SURVEY.md par. 8c, tests/golden/ref_i64_kat.json)
   and, in this container, the reference's compiled CPU functions (oracle/_ref).
-* BN254 Fr / BLS12-381 Fr: the reference never runs a >64-bit modulus, so these are
-  "parity unpinned" by the reference itself; they are anchored by the same algorithm
-  (pinned above on the small field), by the direct DFT definition and by the SHA-256
-  anchors of SURVEY.md par. 8c (tests/golden/anchors.json).
+* BN254 Fr / BLS12-381 Fr: PINNED against the reference's own GPU drivers -- big-num.cu's
+  NTT_GPU_Naive / NTT_GZKP take the modulus as a 256-bit argument; compiled unmodified
+  (oracle/ref256_harness.cu) and run on a B200 they give the digests in
+  tests/golden/ref256_gpu_kat.json, which this oracle reproduces (tests/test_oracle.py).
+  Also anchored by the direct DFT definition and tests/golden/anchors.json.
 
 Each function cites the reference lines it restates.
 """

@@ -709,3 +709,42 @@ def test_u64_limb_view_is_the_same_bytes(torch_cuda, ctxs):
     got64 = d.cpu().numpy().view(np.uint64)
     got = [sum(int(got64[i, k]) << (64 * k) for k in range(4)) for i in range(1 << log_n)]
     assert got == po.ntt_ref(vals, po.BLS12_381_FR)
+
+
+# --------------------------------------------------------------------------- the reference's GPU drivers
+def test_library_matches_the_reference_gpu_golden_vectors(torch_cuda, ctxs):
+    """tests/golden/ref256_gpu_kat.json (the reference's own NTT_GPU_Naive / NTT_GZKP run on a B200
+    for p = 469762049, BN254 Fr, BLS12-381 Fr): the CUDA path must give the same bytes."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    with open(os.path.join(GOLD, "ref256_gpu_kat.json")) as f:
+        kat = json.load(f)
+    for case in kat["cases"]:
+        p, g = FIELDS[case["field"]]
+        n = 1 << case["log_n"]
+        if case["input"] == "iota":
+            x = np.zeros((n, 8), dtype=np.uint32)
+            x[:, 0] = np.arange(n, dtype=np.uint32)
+        else:
+            x = co.splitmix_elements(n, p, case["seed"])
+        got = _gpu_forward(torch_cuda, ctxs(case["field"], 20), x, case["log_n"])
+        assert hashlib.sha256(got.tobytes()).hexdigest() == case["sha256_gzkp"], (case["field"], case["log_n"], case["input"])
+
+
+def test_library_against_the_reference_gpu_drivers_live(torch_cuda, ctxs):
+    """When oracle/_ref/libref256.so travelled to the box (built where /root/reference exists): run the
+    reference's NTT_GPU_Naive and NTT_GZKP and this library side by side on fresh random inputs."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    if co.ref256_lib() is None:
+        pytest.skip("oracle/_ref/libref256.so not present (built only where /root/reference exists)")
+    rng = np.random.default_rng()
+    for field in ("bn254_fr", "bls12_381_fr"):
+        p, g = FIELDS[field]
+        for log_n in (5, 9, 13, 17):
+            x = co.splitmix_elements(1 << log_n, p, int(rng.integers(1, 2**31)))
+            ours = _gpu_forward(torch_cuda, ctxs(field, 20), x, log_n)
+            for driver in (0, 1):
+                assert np.array_equal(co.ref256_ntt(x, log_n, p, g, driver), ours), (field, log_n, driver)

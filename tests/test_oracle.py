@@ -136,3 +136,34 @@ def test_c_oracle_helpers(built):
     assert co.array_to_ints(s) == [(a + b) % F.p for a, b in zip(co.array_to_ints(x), co.array_to_ints(y))]
     with pytest.raises(ValueError):
         co.ntt(co.ints_to_array(range(8)), 469762049 * 2 + 1, 3)  # 2^3 does not divide p-1 = 2*469762049
+
+
+def _ref256_input(case, p):
+    n = 1 << case["log_n"]
+    if case["input"] == "iota":
+        x = np.zeros((n, 8), dtype=np.uint32)
+        x[:, 0] = np.arange(n, dtype=np.uint32)
+        return x
+    return co.splitmix_elements(n, p, case["seed"])
+
+
+def test_oracle_matches_the_reference_gpu_drivers_on_the_big_fields(built):
+    """tests/golden/ref256_gpu_kat.json: outputs of the reference's OWN 256-bit GPU drivers
+    (NTT_GPU_Naive / NTT_GZKP of big-num.cu, compiled unmodified, run on a B200 by
+    scripts/gen_golden_ref256.py) on p = 469762049, BN254 Fr and BLS12-381 Fr, x[j] = j and random
+    inputs, 2^5 .. 2^16 points.  The oracle must reproduce every digest: this is what pins parity on
+    the >64-bit fields to the reference's code rather than to a restatement of it."""
+    kat = _load("ref256_gpu_kat.json")
+    assert len(kat["cases"]) >= 40
+    fields = {"ref29": po.REF29, "bn254_fr": po.BN254_FR, "bls12_381_fr": po.BLS12_381_FR}
+    for case in kat["cases"]:
+        assert case["drivers_agree"] and case["sha256_naive"] == case["sha256_gzkp"]
+        F = fields[case["field"]]
+        x = _ref256_input(case, F.p)
+        got = co.ntt(x, F.p, F.g, threads=4)
+        assert hashlib.sha256(got.tobytes()).hexdigest() == case["sha256_naive"], (case["field"], case["log_n"], case["input"])
+        assert [hex(sum(int(got[i][k]) << (32 * k) for k in range(8))) for i in range(4)] == case["first"]
+        if case["log_n"] <= 8:  # the Python-int statement as well
+            xi = [sum(int(x[i][k]) << (32 * k) for k in range(8)) for i in range(len(x))]
+            want = po.ntt_ref(xi, F)
+            assert [sum(int(got[i][k]) << (32 * k) for k in range(8)) for i in range(len(x))] == want
