@@ -203,6 +203,9 @@ def run_reference_gpu(args):
         if m.group(1) == "GZKP":
             rows.append(cur)
             cur = {}
+    if not rows or min(rows[-1].get("naive", 0.0), rows[-1].get("GZKP", 0.0)) <= 0.0:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref/ref_bignum produced no kernel timings (no CUDA device?)"}))
+        return
     for i, r in enumerate(rows):
         r["log_n"] = 5 + i  # the program sweeps kk = 5..24 (big-num.cu:370)
     last = rows[-1]
