@@ -609,8 +609,9 @@ def test_repeated_runs_are_bitwise_identical(torch_cuda, ctxs):
 
 
 def test_2p26_properties(torch_cuda):
-    """A transform beyond the streamed-twiddle limit (two-factor first pass, 5 passes, 2 GiB of
-    data): one output sampled by Horner on the CPU, and the round trip on the device."""
+    """2 GiB of data, 5 passes, a 2 GiB streamed first-pass twiddle array (the two-lookup alternative
+    is covered by test_streamed_and_two_lookup_twiddles_agree): one output sampled by Horner on the
+    CPU, and the round trip on the device."""
     from ntt_b200.api import FIELDS, Ntt256
     from oracle import c_oracle as co
 
@@ -627,6 +628,39 @@ def test_2p26_properties(torch_cuda):
     got = d[8 * k: 8 * k + 8].cpu().numpy().view(np.uint32)
     assert co.dft_sample(x, p, g, k) == sum(int(got[i]) << (32 * i) for i in range(8))
     ctx.inverse(d, log_n)
+    torch.cuda.synchronize()
+    assert torch.equal(d, src)
+    ctx.close()
+
+
+def test_maximum_size_2p28_closed_form(torch_cuda):
+    """BASELINE config 5's size on ONE GPU, the largest transform BN254 Fr admits (two-adicity 28;
+    8 GiB of data).  Dense input with a closed form: x[j] = c*h^j (made by the coset entry point from
+    a constant array), so X[k] = c*(h^n - 1)/(h*w_n^k - 1) -- every output is checked-able exactly
+    without a second 2^28-point transform; sampled k, then the inverse restores the constant array."""
+    from ntt_b200.api import FIELDS, Ntt256
+
+    torch = torch_cuda
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < (40 << 30):
+        pytest.skip("needs ~34 GiB of device memory")
+    p, g = FIELDS["bn254_fr"]
+    log_n = 28
+    n = 1 << log_n
+    c, h = 0x1234567890ABCDEF1122334455667788 % p, 7
+    ctx = Ntt256("bn254_fr", max_log_n=log_n)
+    limbs = torch.tensor([(c >> (32 * k)) & 0xFFFFFFFF for k in range(8)], dtype=torch.int64).to(torch.int32)
+    src = limbs.cuda().repeat(n)  # 8 GiB
+    d = src.clone()
+    ctx.coset_forward(d, log_n, h)
+    torch.cuda.synchronize()
+    w = pow(g, (p - 1) >> log_n, p)
+    num = c * (pow(h, n, p) - 1) % p
+    for k in (0, 1, 2, n // 3, n // 2, n - 1, 0x0ABCDEF, 0xFEDCBA9):
+        got = d[8 * k: 8 * k + 8].cpu().numpy().view(np.uint32)
+        want = num * pow((h * pow(w, k, p) - 1) % p, p - 2, p) % p
+        assert sum(int(got[i]) << (32 * i) for i in range(8)) == want, k
+    ctx.coset_inverse(d, log_n, h)
     torch.cuda.synchronize()
     assert torch.equal(d, src)
     ctx.close()
