@@ -71,6 +71,7 @@ struct ntt256_ctx {
     U256 shift;
     int log_n, lo_bits;
     uint4 *hi, *lo;
+    uint4* direct;  // s^j for every j < 2^log_n (32 B * 2^log_n), or null: see kCosetDirect* below
   };
   std::vector<CosetTables> cosets;        // small cache of shift^j tables (forward and inverse shifts)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // pipelined host batches
@@ -524,17 +525,27 @@ int transform_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, in
   return NTT256_OK;
 }
 
+// Multiplied-out shift^j tables trade 32 B/element of memory and HBM traffic for one of the two
+// products of the scaling pass (2^24: 0.53 -> 0.3 ms).  One table may take 1 GiB (n <= 2^25), all
+// cached ones together 2 GiB; larger transforms keep the two small factored tables.
+constexpr size_t kCosetDirectMax = (size_t)1 << 30;
+constexpr size_t kCosetDirectBudget = (size_t)2 << 30;
+
+void drop_oldest_coset(ntt256_ctx* ctx) {
+  auto& c = ctx->cosets.front();
+  cudaFree(c.hi);
+  cudaFree(c.lo);
+  if (c.direct) cudaFree(c.direct);
+  ctx->cosets.erase(ctx->cosets.begin());
+}
+
 int get_coset_tables(ntt256_ctx* ctx, const U256& shift_plain, int log_n, const ntt256_ctx::CosetTables** out) {
   for (auto& c : ctx->cosets)
     if (c.log_n == log_n && u256_cmp(c.shift, shift_plain) == 0) {
       *out = &c;
       return NTT256_OK;
     }
-  if (ctx->cosets.size() >= 8) {
-    cudaFree(ctx->cosets.front().hi);
-    cudaFree(ctx->cosets.front().lo);
-    ctx->cosets.erase(ctx->cosets.begin());
-  }
+  if (ctx->cosets.size() >= 8) drop_oldest_coset(ctx);
   ntt256_ctx::CosetTables t;
   t.shift = shift_plain;
   t.log_n = log_n;
@@ -545,6 +556,27 @@ int get_coset_tables(ntt256_ctx* ctx, const U256& shift_plain, int log_n, const 
   if (rc) return rc;
   rc = build_power_table(ctx, &t.hi, pow2k(ctx->hf, sm, t.lo_bits), log_n - t.lo_bits);
   if (rc) return rc;
+  t.direct = nullptr;
+  const size_t dbytes = (size_t)32 << log_n;
+  if (dbytes <= kCosetDirectMax) {
+    auto cached = [&] {
+      size_t sum = 0;
+      for (auto& c : ctx->cosets)
+        if (c.direct) sum += (size_t)32 << c.log_n;
+      return sum;
+    };
+    while (!ctx->cosets.empty() && cached() + dbytes > kCosetDirectBudget) drop_oldest_coset(ctx);
+    if (cudaMalloc((void**)&t.direct, dbytes) == cudaSuccess) {
+      const unsigned long long count = 1ull << log_n;
+      coset_table_kernel<<<(unsigned)((count + 127) / 128), 128>>>(t.direct, count, t.lo_bits, t.hi, t.lo, ctx->fp);
+      ++ctx->launches;
+      CTX_CUDA(cudaGetLastError());
+      CTX_CUDA(cudaDeviceSynchronize());  // one-off: later calls may use any stream
+    } else {
+      cudaGetLastError();  // no memory to spare: keep the factored tables
+      t.direct = nullptr;
+    }
+  }
   ctx->cosets.push_back(t);
   *out = &ctx->cosets.back();
   return NTT256_OK;
@@ -556,8 +588,12 @@ int coset_scale(ntt256_ctx* ctx, void* d_data, int log_n, int batch, const U256&
   if (rc) return rc;
   const unsigned long long n = (unsigned long long)batch << log_n;
   const int threads = 128;
-  coset_scale_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>((uint4*)d_data, n, log_n, t->lo_bits,
-                                                                                      t->hi, t->lo, ctx->fp);
+  if (t->direct)
+    coset_scale_direct_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>((uint4*)d_data, n, log_n,
+                                                                                             t->direct, ctx->fp);
+  else
+    coset_scale_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>((uint4*)d_data, n, log_n,
+                                                                                      t->lo_bits, t->hi, t->lo, ctx->fp);
   ++ctx->launches;
   CTX_CUDA(cudaGetLastError());
   return NTT256_OK;
@@ -679,6 +715,7 @@ void ntt256_ctx_destroy(ntt256_ctx* ctx) {
   for (auto& c : ctx->cosets) {
     cudaFree(c.hi);
     cudaFree(c.lo);
+    if (c.direct) cudaFree(c.direct);
   }
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);

@@ -464,6 +464,34 @@ __global__ void coset_scale_kernel(uint4* __restrict__ data, unsigned long long 
   st_global_256(data + 2 * i, x);
 }
 
+// table[j] <- s^j in Montgomery form, j < count: the two factored tables multiplied out once, so that
+// the scaling pass of a coset transform is one product per element instead of two.
+__global__ void coset_table_kernel(uint4* __restrict__ table, unsigned long long count, int lo_bits,
+                                   const uint4* __restrict__ hi, const uint4* __restrict__ lo,
+                                   const __grid_constant__ FieldParams f) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u32 a[8], b[8];
+  ld_table(a, hi, (u32)(i >> lo_bits));
+  ld_table(b, lo, (u32)i & ((1u << lo_bits) - 1u));
+  mul_by(a, b, f);  // (s^hi R)(s^lo R)/R = s^j R
+  canonicalize(a, f);
+  st_global_256(table + 2 * i, a);
+}
+
+// x[j] <- s^j * x[j] with s^j read from the multiplied-out table (one coalesced 256-bit read).
+__global__ void coset_scale_direct_kernel(uint4* __restrict__ data, unsigned long long n, int log_n,
+                                          const uint4* __restrict__ table, const __grid_constant__ FieldParams f) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 x[8], w[8];
+  ld_global_256(x, data + 2 * i);
+  ld_global_256(w, table + 2 * (i & ((1ull << log_n) - 1ull)));
+  mul_by(x, w, f);
+  canonicalize(x, f);
+  st_global_256(data + 2 * i, x);
+}
+
 // out[i] = c * in[i]  (c Montgomery-form constant): scaled copies of small tables.
 __global__ void table_scale_kernel(uint4* __restrict__ out, const uint4* __restrict__ in, unsigned long long count,
                                    const __grid_constant__ FieldParams f, const __grid_constant__ Fe c) {
