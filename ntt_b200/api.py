@@ -251,6 +251,73 @@ def NTT_GPU_Naive(data, length: int, reverse=None, reverse_len: int = 0, prime=N
     return NTT_GZKP(data, length, reverse, reverse_len, prime, omega, 0, 0, stream)
 
 
+# 384-bit fields (include/ntt384.h): name -> (p, generator)
+FIELDS384 = {
+    # BLS12-377 base field = BW6-761 scalar field: 377 bits, 2^46 | p - 1, generator 15 (arkworks)
+    "bls12_377_fq": (0x01AE3A4617C510EAC63B05C06CA1493B1A22D9F300F5138F1EF3622FBA094800170B5D44300000008508C00000000001, 15),
+}
+
+
+class Ntt384:
+    """ntt384_ctx: forward / inverse NTT over a prime field in 384-bit containers (12 LE u32 limbs,
+    48 bytes per element, canonical residues), one GPU; the reference's `bits` template parameter
+    (big-num.cu:57,67,172,260) at 384."""
+
+    def __init__(self, field="bls12_377_fq", max_log_n: int = 20, device: int = 0, p=None, g=None):
+        L = _load_lib()
+        self._L = L
+        self._h = ctypes.c_void_p()
+        if p is None:
+            p, g = FIELDS384[field]
+        self.p, self.g = int(p), int(g)
+        self.max_log_n = max_log_n
+        pl = np.array([(self.p >> (32 * i)) & 0xFFFFFFFF for i in range(12)], dtype=np.uint32)
+        gl = np.array([(self.g >> (32 * i)) & 0xFFFFFFFF for i in range(12)], dtype=np.uint32)
+        rc = L.ntt384_ctx_create(ctypes.byref(self._h), device, _u32p(pl), _u32p(gl), max_log_n)
+        if rc:
+            raise Ntt256Error(rc)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.ntt384_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc:
+            raise Ntt256Error(rc, self._L.ntt384_last_cuda_error(self._h).decode())
+
+    @staticmethod
+    def _ptr(data, n_elements: int) -> int:
+        if data.numel() * data.element_size() != n_elements * 48 or not data.is_cuda or not data.is_contiguous():
+            raise ValueError(f"expected a contiguous CUDA tensor of {n_elements} elements of 48 bytes")
+        return data.data_ptr()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.ntt384_launch_count(self._h))
+
+    def forward(self, data, log_n: int, batch: int = 1, stream=None):
+        self._check(self._L.ntt384_forward_batch(self._h, self._ptr(data, batch << log_n), log_n, batch, _stream_handle(stream)))
+        return data
+
+    def inverse(self, data, log_n: int, batch: int = 1, stream=None):
+        self._check(self._L.ntt384_inverse_batch(self._h, self._ptr(data, batch << log_n), log_n, batch, _stream_handle(stream)))
+        return data
+
+    def vec_mul(self, a, b, out=None, mont_form: bool = False, stream=None):
+        n = a.numel() * a.element_size() // 48
+        out = a if out is None else out
+        self._check(self._L.ntt384_vec_mul(self._h, self._ptr(out, n), self._ptr(a, n), self._ptr(b, n), n, int(mont_form),
+                                           _stream_handle(stream)))
+        return out
+
+
 class Ntt256MultiGpu:
     """ntt256_mgpu: one host thread driving several peer-connected GPUs (no NCCL, no extra
     processes).  Shards are torch CUDA tensors, one per device, in the four-step layouts of

@@ -1,0 +1,315 @@
+// C ABI of the 384-bit transforms (include/ntt384.h): the reference's `bits` template parameter
+// (/root/reference/src/big-num.cu:57,67,172,260) instantiated at 384 -- fields such as BLS12-377 Fq
+// (= BW6-761 Fr; 377 bits, 2-adicity 46).  Same planner and pass structure as the 256-bit library
+// (plan.cpp, ntt_kernels_n.cuh), field layer field_n.cuh with 12 limbs.  First cut of SURVEY.md
+// par. 8f row 4: forward / inverse / batches on one GPU and the element-wise product.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ntt384.h"
+#include "hostfield_n.h"
+#include "ntt_kernels_n.cuh"
+#include "plan.h"
+
+using namespace ntt256;
+
+namespace {
+constexpr int NL = 12;
+constexpr int W = 6;
+typedef UIntN<W> U384;
+constexpr int kTileBits384 = 10;   // 48 KiB of shared memory, 256 threads: two CTAs per SM
+constexpr int kCoalesce384 = 2;    // runs of >= 4 elements = 192 bytes
+constexpr int kHiBits384 = 16;     // 2^16 x 48 B = 3 MiB
+constexpr int kLocBits384 = 12;
+}  // namespace
+
+struct ntt384_ctx {
+  int device = 0;
+  int max_log_n = 0;
+  HostFieldN<W> hf;
+  FieldParamsN<NL> fp;
+  U384 wN, wN_inv;
+  uint4 *om_hi = nullptr, *om_lo = nullptr, *loc = nullptr;
+  int hi_bits = 0, lo_bits = 0, loc_bits = 0;
+  u32 c8[2][3][NL];
+  u32 w4[2][NL];
+  U384 ninv[64];
+  bool ninv_ok[64] = {};
+  std::map<int, Plan> plans;  // by log_n
+  unsigned long long launches = 0;
+  std::string last_err;
+};
+
+namespace {
+
+#define CTX_CUDA(call)                                                     \
+  do {                                                                     \
+    cudaError_t e_ = (call);                                               \
+    if (e_ != cudaSuccess) {                                               \
+      ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(e_);  \
+      return NTT256_ERR_CUDA;                                              \
+    }                                                                      \
+  } while (0)
+
+U384 pow2k(const HostFieldN<W>& hf, U384 b, int k) {
+  for (int i = 0; i < k; ++i) b = hf.mul(b, b);
+  return b;
+}
+
+int build_power_table(ntt384_ctx* ctx, uint4** out, const U384& base_mont, int bits) {
+  const unsigned long long count = 1ull << bits;
+  CTX_CUDA(cudaMalloc((void**)out, count * 4 * NL));
+  std::vector<u32> pw((size_t)NL * 64, 0);
+  U384 b = base_mont;
+  for (int k = 0; k < std::max(bits, 1); ++k) {
+    un_to_limbs<W>(b, &pw[(size_t)NL * k]);
+    b = ctx->hf.mul(b, b);
+  }
+  uint4* d_pw = nullptr;
+  CTX_CUDA(cudaMalloc((void**)&d_pw, pw.size() * 4));
+  CTX_CUDA(cudaMemcpy(d_pw, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));
+  FeN<NL> one;
+  un_to_limbs<W>(ctx->hf.one, one.v);
+  const int threads = 128;
+  twiddle_powers_kernel_n<NL><<<(unsigned)((count + threads - 1) / threads), threads>>>(*out, d_pw, bits, count, ctx->fp, one);
+  ++ctx->launches;
+  CTX_CUDA(cudaGetLastError());
+  CTX_CUDA(cudaDeviceSynchronize());
+  CTX_CUDA(cudaFree(d_pw));
+  return NTT256_OK;
+}
+
+int get_plan(ntt384_ctx* ctx, int log_n, const Plan** out) {
+  auto it = ctx->plans.find(log_n);
+  if (it == ctx->plans.end()) {
+    PlanRequest req;
+    req.log_n = log_n;
+    req.tile_bits = std::min(kTileBits384, log_n);
+    req.coalesce_bits = std::min(kCoalesce384, req.tile_bits);
+    req.max_log_n = ctx->max_log_n;
+    req.group_bits = 2;
+    Plan plan;
+    bool ok = make_plan(req, &plan);
+    for (int g = req.coalesce_bits - 1; !ok && g >= 0; --g) {
+      req.coalesce_bits = g;
+      ok = make_plan(req, &plan, 12);
+    }
+    for (int t = req.tile_bits + 1; !ok && t <= 11; ++t) {
+      req.tile_bits = t;
+      ok = make_plan(req, &plan, 12);
+    }
+    if (!ok) return NTT256_ERR_PLAN;
+    it = ctx->plans.emplace(log_n, plan).first;
+  }
+  *out = &it->second;
+  return NTT256_OK;
+}
+
+const U384& inv_pow2(ntt384_ctx* ctx, int k) {
+  if (!ctx->ninv_ok[k]) {
+    ctx->ninv[k] = ctx->hf.inv(ctx->hf.to_mont(un_small<W>(1ull << k)));
+    ctx->ninv_ok[k] = true;
+  }
+  return ctx->ninv[k];
+}
+
+int transform(ntt384_ctx* ctx, void* d_data, int log_n, int batch, bool inverse, cudaStream_t stream) {
+  if (!ctx || !d_data || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  if (log_n == 0) return NTT256_OK;
+  if (log_n < 3) {
+    TinyArgsN<NL> A;
+    std::memset(&A, 0, sizeof(A));
+    A.f = ctx->fp;
+    A.log_n = log_n;
+    std::memcpy(A.w4, ctx->w4[inverse ? 1 : 0], sizeof(A.w4));
+    A.do_scale = inverse ? 1 : 0;
+    if (inverse) un_to_limbs<W>(inv_pow2(ctx, log_n), A.scale);
+    A.batch = (unsigned long long)batch;
+    const int threads = 128;
+    ntt_tiny_kernel_n<NL><<<(unsigned)((A.batch + threads - 1) / threads), threads, 0, stream>>>((uint4*)d_data, A);
+    ++ctx->launches;
+    CTX_CUDA(cudaGetLastError());
+    return NTT256_OK;
+  }
+  const Plan* plan = nullptr;
+  int rc = get_plan(ctx, log_n, &plan);
+  if (rc) return rc;
+  PassArgsN<NL> A;
+  std::memset(&A, 0, sizeof(A));
+  A.f = ctx->fp;
+  A.om_hi = ctx->om_hi;
+  A.om_lo = ctx->om_lo;
+  A.loc = ctx->loc;
+  A.hi_bits = ctx->hi_bits;
+  A.lo_bits = ctx->lo_bits;
+  A.loc_bits = ctx->loc_bits;
+  A.inverse = inverse ? 1 : 0;
+  std::memcpy(A.c8, ctx->c8[inverse ? 1 : 0], sizeof(A.c8));
+  A.batch_stride = 1ull << log_n;
+  if (inverse) un_to_limbs<W>(inv_pow2(ctx, log_n), A.scale);
+  const int kSlice = 65535;
+  for (int b0 = 0; b0 < batch; b0 += kSlice) {
+    const int nb = std::min(kSlice, batch - b0);
+    uint4* p = (uint4*)d_data + (size_t)(NL / 4) * ((size_t)b0 << log_n);
+    for (size_t i = 0; i < plan->passes.size(); ++i) {
+      A.pd = plan->passes[i];
+      if (inverse && i + 1 == plan->passes.size()) A.pd.scale_out = 1;
+      const int T = A.pd.T;
+      const unsigned long long nblk = 1ull << A.pd.nblk_bits;
+      if (nblk > 0x7fffffffull) return NTT256_ERR_ARG;
+      dim3 grid((unsigned)nblk, (unsigned)nb, 1);
+      ntt384_pass_kernel<<<grid, 1u << (T - 2), (size_t)(4 * NL) << T, stream>>>(p, A);
+      ++ctx->launches;
+      CTX_CUDA(cudaGetLastError());
+    }
+  }
+  return NTT256_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ntt384_ctx_create(ntt384_ctx** out, int device, const uint32_t p[12], const uint32_t g[12], int max_log_n) {
+  if (!out || !p || !g || max_log_n < 1 || max_log_n > 30) return NTT256_ERR_ARG;
+  *out = nullptr;
+  U384 P = un_from_limbs<W>(p), G = un_from_limbs<W>(g);
+  if (!(P.w[0] & 1) || un_bitlen(P) > 32 * NL - 1 || un_bitlen(P) < 2) return NTT256_ERR_FIELD;
+  if (un_is_zero(G) || un_cmp(G, P) >= 0) return NTT256_ERR_FIELD;
+  U384 pm1;
+  un_sub(pm1, P, un_small<W>(1));
+  for (int i = 0; i < max_log_n; ++i)
+    if (un_bit(pm1, i)) return NTT256_ERR_FIELD;
+  ntt384_ctx* ctx = new (std::nothrow) ntt384_ctx();
+  if (!ctx) return NTT256_ERR_NOMEM;
+  ctx->device = device;
+  ctx->max_log_n = max_log_n;
+  ctx->hf.init(P);
+  std::memset(&ctx->fp, 0, sizeof(ctx->fp));
+  un_to_limbs<W>(P, ctx->fp.p);
+  U384 P2;
+  un_add(P2, P, P);
+  un_to_limbs<W>(P2, ctx->fp.p2);
+  ctx->fp.np0 = (u32)ctx->hf.np0;
+  // w_N = g^((p-1)/N), must have exact order N
+  U384 gm = ctx->hf.to_mont(G);
+  ctx->wN = ctx->hf.pow(gm, un_shr(pm1, max_log_n));
+  ctx->wN_inv = ctx->hf.inv(ctx->wN);
+  {
+    U384 h = pow2k(ctx->hf, ctx->wN, max_log_n - 1);
+    U384 m1 = ctx->hf.sub(un_small<W>(0), ctx->hf.one);
+    if (un_cmp(h, m1) != 0) {
+      delete ctx;
+      return NTT256_ERR_FIELD;
+    }
+  }
+  ctx->hi_bits = std::min(max_log_n, kHiBits384);
+  ctx->lo_bits = max_log_n - ctx->hi_bits;
+  ctx->loc_bits = std::min(max_log_n, kLocBits384);
+  std::memset(ctx->c8, 0, sizeof(ctx->c8));
+  std::memset(ctx->w4, 0, sizeof(ctx->w4));
+  if (max_log_n >= 3) {
+    U384 w8 = pow2k(ctx->hf, ctx->wN, max_log_n - 3), w8i = pow2k(ctx->hf, ctx->wN_inv, max_log_n - 3);
+    U384 a = w8, b = w8i;
+    for (int k = 0; k < 3; ++k) {
+      un_to_limbs<W>(a, ctx->c8[0][k]);
+      un_to_limbs<W>(b, ctx->c8[1][k]);
+      a = ctx->hf.mul(a, w8);
+      b = ctx->hf.mul(b, w8i);
+    }
+  }
+  if (max_log_n >= 2) {
+    un_to_limbs<W>(pow2k(ctx->hf, ctx->wN, max_log_n - 2), ctx->w4[0]);
+    un_to_limbs<W>(pow2k(ctx->hf, ctx->wN_inv, max_log_n - 2), ctx->w4[1]);
+    if (max_log_n < 3) {
+      std::memcpy(ctx->c8[0][1], ctx->w4[0], 4 * NL);
+      std::memcpy(ctx->c8[1][1], ctx->w4[1], 4 * NL);
+    }
+  }
+  auto fail = [&](int code) {
+    ntt384_ctx_destroy(ctx);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTT256_ERR_CUDA);
+  if (cudaFuncSetAttribute(ntt384_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 * NL) << 11) != cudaSuccess)
+    return fail(NTT256_ERR_CUDA);
+  int rc = build_power_table(ctx, &ctx->om_hi, pow2k(ctx->hf, ctx->wN, ctx->lo_bits), ctx->hi_bits);
+  if (rc) return fail(rc);
+  rc = build_power_table(ctx, &ctx->om_lo, ctx->wN, ctx->lo_bits);
+  if (rc) return fail(rc);
+  rc = build_power_table(ctx, &ctx->loc, pow2k(ctx->hf, ctx->wN, max_log_n - ctx->loc_bits), ctx->loc_bits);
+  if (rc) return fail(rc);
+  *out = ctx;
+  return NTT256_OK;
+}
+
+void ntt384_ctx_destroy(ntt384_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->om_hi) cudaFree(ctx->om_hi);
+  if (ctx->om_lo) cudaFree(ctx->om_lo);
+  if (ctx->loc) cudaFree(ctx->loc);
+  delete ctx;
+}
+
+int ntt384_forward_batch(ntt384_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, batch, false, (cudaStream_t)stream);
+}
+int ntt384_inverse_batch(ntt384_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, batch, true, (cudaStream_t)stream);
+}
+int ntt384_forward(ntt384_ctx* ctx, void* d_data, int log_n, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, 1, false, (cudaStream_t)stream);
+}
+int ntt384_inverse(ntt384_ctx* ctx, void* d_data, int log_n, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, 1, true, (cudaStream_t)stream);
+}
+
+int ntt384_vec_mul(ntt384_ctx* ctx, void* d_out, const void* d_a, const void* d_b, unsigned long long n, int mont_form,
+                   ntt256_stream stream) {
+  if (!ctx || !d_out || !d_a || !d_b) return NTT256_ERR_ARG;
+  if (n == 0) return NTT256_OK;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  FeN<NL> r2;
+  un_to_limbs<W>(ctx->hf.r2, r2.v);
+  const int threads = 128;
+  vec_mul_kernel_n<NL><<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      (uint4*)d_out, (const uint4*)d_a, (const uint4*)d_b, n, mont_form, ctx->fp, r2);
+  ++ctx->launches;
+  CTX_CUDA(cudaGetLastError());
+  return NTT256_OK;
+}
+
+unsigned long long ntt384_launch_count(const ntt384_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* ntt384_last_cuda_error(const ntt384_ctx* ctx) { return ctx ? ctx->last_err.c_str() : ""; }
+
+size_t ntt384_plan_describe(int log_n, int max_log_n, char* buf, size_t buf_len) {
+  PlanRequest req;
+  req.log_n = log_n;
+  req.tile_bits = std::min(kTileBits384, log_n);
+  req.coalesce_bits = std::min(kCoalesce384, req.tile_bits);
+  req.max_log_n = max_log_n;
+  req.group_bits = 2;
+  Plan plan;
+  bool ok = make_plan(req, &plan);
+  for (int g = req.coalesce_bits - 1; !ok && g >= 0; --g) {
+    req.coalesce_bits = g;
+    ok = make_plan(req, &plan, 12);
+  }
+  std::string s = ok ? plan.describe() : std::string("{\"error\": \"no plan\"}");
+  if (buf && buf_len) {
+    size_t m = std::min(buf_len - 1, s.size());
+    std::memcpy(buf, s.data(), m);
+    buf[m] = 0;
+  }
+  return s.size() + 1;
+}
+
+}  // extern "C"

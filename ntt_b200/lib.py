@@ -30,6 +30,13 @@ EXPORTS = [
 ]
 
 
+# every symbol include/ntt384.h declares (the 384-bit companion API, same library)
+EXPORTS384 = [
+    "ntt384_ctx_create", "ntt384_ctx_destroy", "ntt384_forward", "ntt384_inverse", "ntt384_forward_batch",
+    "ntt384_inverse_batch", "ntt384_vec_mul", "ntt384_launch_count", "ntt384_last_cuda_error", "ntt384_plan_describe",
+]
+
+
 class Ntt256Error(RuntimeError):
     def __init__(self, status: int, detail: str = ""):
         self.status = status
@@ -97,6 +104,20 @@ def lib() -> ctypes.CDLL:
         L.ntt256_last_cuda_error.argtypes = [vp]
         L.ntt256_last_cuda_error.restype = ctypes.c_char_p
         L.ntt256_version.restype = ctypes.c_char_p
+        L.ntt384_ctx_create.argtypes = [ctypes.POINTER(vp), ci, u32p, u32p, ci]
+        L.ntt384_ctx_destroy.argtypes = [vp]
+        L.ntt384_ctx_destroy.restype = None
+        for name in ("ntt384_forward", "ntt384_inverse"):
+            getattr(L, name).argtypes = [vp, vp, ci, vp]
+        for name in ("ntt384_forward_batch", "ntt384_inverse_batch"):
+            getattr(L, name).argtypes = [vp, vp, ci, ci, vp]
+        L.ntt384_vec_mul.argtypes = [vp, vp, vp, vp, ctypes.c_ulonglong, ci, vp]
+        L.ntt384_launch_count.argtypes = [vp]
+        L.ntt384_launch_count.restype = ctypes.c_ulonglong
+        L.ntt384_last_cuda_error.argtypes = [vp]
+        L.ntt384_last_cuda_error.restype = ctypes.c_char_p
+        L.ntt384_plan_describe.argtypes = [ci, ci, ctypes.c_char_p, ctypes.c_size_t]
+        L.ntt384_plan_describe.restype = ctypes.c_size_t
         _LIB = L
     return _LIB
 
@@ -123,4 +144,15 @@ def plan_describe_fourstep(step: int, log_n: int, log_r: int, log_p: int, rank: 
     need = L.ntt256_plan_describe_fourstep(*a, None, 0)
     buf = ctypes.create_string_buffer(need)
     L.ntt256_plan_describe_fourstep(*a, buf, need)
+    return json.loads(buf.value.decode())
+
+
+def plan_describe_384(log_n: int, max_log_n: int) -> dict:
+    """Host-only: the pass plan ntt384_forward would run for 2^log_n points (JSON -> dict)."""
+    import json
+
+    L = lib()
+    need = L.ntt384_plan_describe(log_n, max_log_n, None, 0)
+    buf = ctypes.create_string_buffer(need)
+    L.ntt384_plan_describe(log_n, max_log_n, buf, need)
     return json.loads(buf.value.decode())

@@ -51,6 +51,11 @@ BN254_FR = Field(
 BLS12_381_FR = Field(
     "bls12_381_fr", 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001, 7
 )
+# 384-bit containers (include/ntt384.h): BLS12-377 base field = BW6-761 scalar field, generator 15
+BLS12_377_FQ = Field(
+    "bls12_377_fq",
+    0x01AE3A4617C510EAC63B05C06CA1493B1A22D9F300F5138F1EF3622FBA094800170B5D44300000008508C00000000001, 15
+)
 FIELDS = {f.name: f for f in (REF29, BN254_FR, BLS12_381_FR)}
 
 

@@ -24,6 +24,41 @@ def test_exports_match_header(built):
         assert hasattr(L, name), name
 
 
+def test_exports_match_header_384(built):
+    from ntt_b200.lib import EXPORTS384
+
+    with open(os.path.join(ROOT, "include", "ntt384.h")) as f:
+        header = f.read()
+    declared = sorted(set(re.findall(r"\b(ntt384_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(EXPORTS384)
+    L = lib()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_argument_and_field_validation_384(built):
+    from ntt_b200.api import FIELDS384
+    from ntt_b200.lib import ERR_ARG, ERR_FIELD
+
+    L = lib()
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+
+    def create(p, g, max_log_n):
+        h = ctypes.c_void_p()
+        pl = np.array([(p >> (32 * i)) & 0xFFFFFFFF for i in range(12)], dtype=np.uint32)
+        gl = np.array([(g >> (32 * i)) & 0xFFFFFFFF for i in range(12)], dtype=np.uint32)
+        return L.ntt384_ctx_create(ctypes.byref(h), 0, pl.ctypes.data_as(u32p), gl.ctypes.data_as(u32p), max_log_n)
+
+    q, g = FIELDS384["bls12_377_fq"]
+    assert create(q, g, 0) == ERR_ARG
+    assert create(q, g, 31) == ERR_ARG
+    assert create(q - 1, g, 10) == ERR_FIELD            # even
+    assert create((1 << 383) + 1, g, 10) == ERR_FIELD    # no lazy-reduction headroom
+    assert create(q, 4, 10) == ERR_FIELD                 # a square is not a generator
+    assert create(q, g, 47) == ERR_ARG                   # above the API's 2^30 limit (2-adicity is 46)
+    assert L.ntt384_forward(None, None, 3, None) == ERR_ARG
+
+
 def test_strings(built):
     L = lib()
     assert L.ntt256_strerror(0) == b"ok"

@@ -11,8 +11,8 @@ from oracle import py_oracle as po
 M32 = 0xFFFFFFFF
 
 
-def _limbs(v):
-    return [(v >> (32 * i)) & M32 for i in range(8)]
+def _limbs(v, nl=8):
+    return [(v >> (32 * i)) & M32 for i in range(nl)]
 
 
 def _val(l):
@@ -24,9 +24,9 @@ class Overflow(Exception):
 
 
 def _mad_row(acc, a4, b):
-    """acc[0..7] += (a4[0..3]) * b laid at limb pairs; returns carry out (as mad_row in field.cuh)."""
+    """acc[0..NL) += (a4[0..NL/2)) * b laid at limb pairs; returns carry out (as mad_row in field.cuh)."""
     c = 0
-    for j in range(4):
+    for j in range(len(a4)):
         prod = a4[j] * b
         t = acc[2 * j] + (prod & M32) + c
         acc[2 * j] = t & M32
@@ -37,13 +37,15 @@ def _mad_row(acc, a4, b):
     return c
 
 
-def mont_mul_model(a, b, p, np0):
-    al, bl, pl = _limbs(a), _limbs(b), _limbs(p)
+def mont_mul_model(a, b, p, np0, NL=8):
+    """NL = 8: mont_mul in field.cuh; NL = 12: mont_mul_n<12> in field_n.cuh (same chains)."""
+    H = NL // 2
+    al, bl, pl = _limbs(a, NL), _limbs(b, NL), _limbs(p, NL)
     ae, ao = al[0::2], al[1::2]
     pe, podd = pl[0::2], pl[1::2]
-    X = [0] * 8
-    Y = [0] * 8
-    for j in range(4):
+    X = [0] * NL
+    Y = [0] * NL
+    for j in range(H):
         pr = ae[j] * bl[0]
         X[2 * j], X[2 * j + 1] = pr & M32, pr >> 32
         pr = ao[j] * bl[0]
@@ -55,20 +57,20 @@ def mont_mul_model(a, b, p, np0):
         cy = _mad_row(Y, podd, m)
         if cy:
             raise Overflow("odd chain carried out")
-        if Y[7] + cx > M32:
-            raise Overflow("Y[7] overflow on carry fold")
-        Y[7] += cx
+        if Y[NL - 1] + cx > M32:
+            raise Overflow("Y top limb overflow on carry fold")
+        Y[NL - 1] += cx
         assert X[0] == 0
 
     redc()
-    for i in range(1, 8):
+    for i in range(1, NL):
         # shift_mad_row
         t = Y[0] + X[1]
         nX0, c = t & M32, t >> 32
-        nY = [X[2], X[3], X[4], X[5], X[6], X[7], 0, 0]
+        nY = X[2:NL] + [0, 0]
         # nY += a_odd * b_i with carry-in c
         cc = c
-        for j in range(4):
+        for j in range(H):
             pr = ao[j] * bl[i]
             t = nY[2 * j] + (pr & M32) + cc
             nY[2 * j], cc = t & M32, t >> 32
@@ -76,17 +78,17 @@ def mont_mul_model(a, b, p, np0):
             nY[2 * j + 1], cc = t & M32, t >> 32
         if cc:
             raise Overflow("nY chain carried out")
-        nX = [nX0] + Y[1:8]
+        nX = [nX0] + Y[1:NL]
         cx = _mad_row(nX, ae, bl[i])
-        if nY[7] + cx > M32:
-            raise Overflow("nY[7] overflow")
-        nY[7] += cx
+        if nY[NL - 1] + cx > M32:
+            raise Overflow("nY top limb overflow")
+        nY[NL - 1] += cx
         X[:] = nX
         Y[:] = nY
         redc()
     r = _val(Y) + (_val(X) >> 32)
-    if r >> 256:
-        raise Overflow("result exceeds 256 bits")
+    if r >> (32 * NL):
+        raise Overflow("result exceeds the container")
     return r
 
 
@@ -112,6 +114,27 @@ def test_mont_mul_model_value_and_no_overflow(F):
         cases.append((a, b))
     for a, b in cases:
         r = mont_mul_model(a, b, p, np0)  # raises Overflow if a chain carries out
+        assert r < two_p
+        assert r % p == a * b * Rinv % p
+
+
+@pytest.mark.parametrize("F", [po.BLS12_377_FQ, po.Field("p383m187", (1 << 383) - 187, 2)], ids=lambda f: f.name)
+def test_mont_mul_model_12_limbs(F):
+    """field_n.cuh at NL = 12 (384-bit containers): value identity and the no-carry-out claims."""
+    p, NL = F.p, 12
+    np0 = (-pow(p, -1, 1 << 32)) % (1 << 32)
+    Rinv = pow(1 << (32 * NL), -1, p)
+    rng = random.Random(384)
+    two_p = 2 * p
+    cap = 1 << (32 * NL)
+    cases = [(a, b) for a in (0, 1, p - 1, p - 2, p >> 1, M32) for b in (0, 1, p - 1, p, two_p - 1, min(two_p, cap) - 1)]
+    cases += [(rng.randrange(p), rng.randrange(two_p)) for _ in range(1500)]
+    for _ in range(300):
+        a = _val([rng.choice([0, M32, rng.getrandbits(32)]) for _ in range(NL)]) % p
+        b = _val([rng.choice([0, M32, rng.getrandbits(32)]) for _ in range(NL)]) % two_p
+        cases.append((a, b))
+    for a, b in cases:
+        r = mont_mul_model(a, b, p, np0, NL)
         assert r < two_p
         assert r % p == a * b * Rinv % p
 

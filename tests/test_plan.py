@@ -5,7 +5,7 @@ import random
 import pytest
 
 import plan_sim
-from ntt_b200.lib import plan_describe
+from ntt_b200.lib import plan_describe, plan_describe_384
 from oracle import py_oracle as po
 
 
@@ -95,3 +95,16 @@ def test_every_small_configuration_executes_to_the_oracle(built):
                     assert plan_sim.run_plan(want, plan, F.p, F.g, 14, inverse=True) == x, (L, gb, T, g)
                     ok += 1
     assert ok > 700 and noplan < ok // 8
+
+
+@pytest.mark.parametrize("L", [3, 4, 5, 7, 9, 10, 11, 12, 13])
+def test_384_bit_plans_execute_to_the_oracle(built, L):
+    """The plans ntt384_forward runs (four elements per thread, 2^10-element tiles), executed by the
+    kernel model over BLS12-377 Fq."""
+    F = po.BLS12_377_FQ
+    plan = plan_describe_384(L, 14)
+    assert "error" not in plan and plan["group_bits"] == 2
+    rng = random.Random(L)
+    x = [rng.randrange(F.p) for _ in range(1 << L)]
+    want = po.ntt_ref(x, F)
+    assert plan_sim.run_plan(x, plan, F.p, F.g, 14) == want
