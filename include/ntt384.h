@@ -27,6 +27,9 @@ typedef struct ntt384_ctx ntt384_ctx;
 /* p odd, p < 2^383, 2^max_log_n | p - 1, g a generator (checked: w_N^(N/2) == -1); max_log_n <= 30. */
 int ntt384_ctx_create(ntt384_ctx** out, int device, const uint32_t p[12], const uint32_t g[12], int max_log_n);
 void ntt384_ctx_destroy(ntt384_ctx* ctx);
+/* Plan tuning (optional): tile_bits in [3,11] (shared-memory tile = 2^tile_bits elements of 48 bytes;
+ * default 9), coalesce_bits in [0,6] (global access runs of >= 2^coalesce_bits elements; default 1). */
+int ntt384_ctx_set_tuning(ntt384_ctx* ctx, int tile_bits, int coalesce_bits);
 
 int ntt384_forward(ntt384_ctx* ctx, void* d_data, int log_n, ntt256_stream stream);
 int ntt384_inverse(ntt384_ctx* ctx, void* d_data, int log_n, ntt256_stream stream); /* includes 1/n */

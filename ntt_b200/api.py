@@ -292,6 +292,9 @@ class Ntt384:
         if rc:
             raise Ntt256Error(rc, self._L.ntt384_last_cuda_error(self._h).decode())
 
+    def set_tuning(self, tile_bits: int, coalesce_bits: int):
+        self._check(self._L.ntt384_ctx_set_tuning(self._h, tile_bits, coalesce_bits))
+
     @staticmethod
     def _ptr(data, n_elements: int) -> int:
         if data.numel() * data.element_size() != n_elements * 48 or not data.is_cuda or not data.is_contiguous():

@@ -23,8 +23,8 @@ namespace {
 constexpr int NL = 12;
 constexpr int W = 6;
 typedef UIntN<W> U384;
-constexpr int kTileBits384 = 10;   // 48 KiB of shared memory, 256 threads: two CTAs per SM
-constexpr int kCoalesce384 = 2;    // runs of >= 4 elements = 192 bytes
+constexpr int kTileBits384 = 9;    // 24 KiB of shared memory, 128 threads (sweep: profiles/r01_ntt384.jsonl)
+constexpr int kCoalesce384 = 1;    // runs of >= 2 elements = 96 bytes
 constexpr int kHiBits384 = 16;     // 2^16 x 48 B = 3 MiB
 constexpr int kLocBits384 = 12;
 }  // namespace
@@ -41,6 +41,7 @@ struct ntt384_ctx {
   u32 w4[2][NL];
   U384 ninv[64];
   bool ninv_ok[64] = {};
+  int tile_bits = kTileBits384, coalesce_bits = kCoalesce384;
   std::map<int, Plan> plans;  // by log_n
   unsigned long long launches = 0;
   std::string last_err;
@@ -90,8 +91,8 @@ int get_plan(ntt384_ctx* ctx, int log_n, const Plan** out) {
   if (it == ctx->plans.end()) {
     PlanRequest req;
     req.log_n = log_n;
-    req.tile_bits = std::min(kTileBits384, log_n);
-    req.coalesce_bits = std::min(kCoalesce384, req.tile_bits);
+    req.tile_bits = std::min(ctx->tile_bits, log_n);
+    req.coalesce_bits = std::min(ctx->coalesce_bits, req.tile_bits);
     req.max_log_n = ctx->max_log_n;
     req.group_bits = 2;
     Plan plan;
@@ -257,6 +258,15 @@ void ntt384_ctx_destroy(ntt384_ctx* ctx) {
   if (ctx->om_lo) cudaFree(ctx->om_lo);
   if (ctx->loc) cudaFree(ctx->loc);
   delete ctx;
+}
+
+int ntt384_ctx_set_tuning(ntt384_ctx* ctx, int tile_bits, int coalesce_bits) {
+  if (!ctx || tile_bits < 3 || tile_bits > 11 || coalesce_bits < 0 || coalesce_bits > 6 || coalesce_bits > tile_bits)
+    return NTT256_ERR_ARG;
+  ctx->tile_bits = tile_bits;
+  ctx->coalesce_bits = coalesce_bits;
+  ctx->plans.clear();
+  return NTT256_OK;
 }
 
 int ntt384_forward_batch(ntt384_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream) {

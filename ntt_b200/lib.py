@@ -32,7 +32,7 @@ EXPORTS = [
 
 # every symbol include/ntt384.h declares (the 384-bit companion API, same library)
 EXPORTS384 = [
-    "ntt384_ctx_create", "ntt384_ctx_destroy", "ntt384_forward", "ntt384_inverse", "ntt384_forward_batch",
+    "ntt384_ctx_create", "ntt384_ctx_destroy", "ntt384_ctx_set_tuning", "ntt384_forward", "ntt384_inverse", "ntt384_forward_batch",
     "ntt384_inverse_batch", "ntt384_vec_mul", "ntt384_launch_count", "ntt384_last_cuda_error", "ntt384_plan_describe",
 ]
 
@@ -107,6 +107,7 @@ def lib() -> ctypes.CDLL:
         L.ntt384_ctx_create.argtypes = [ctypes.POINTER(vp), ci, u32p, u32p, ci]
         L.ntt384_ctx_destroy.argtypes = [vp]
         L.ntt384_ctx_destroy.restype = None
+        L.ntt384_ctx_set_tuning.argtypes = [vp, ci, ci]
         for name in ("ntt384_forward", "ntt384_inverse"):
             getattr(L, name).argtypes = [vp, vp, ci, vp]
         for name in ("ntt384_forward_batch", "ntt384_inverse_batch"):
