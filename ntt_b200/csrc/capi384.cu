@@ -43,6 +43,7 @@ struct ntt384_ctx {
   bool ninv_ok[64] = {};
   int tile_bits = kTileBits384, coalesce_bits = kCoalesce384;
   std::map<int, Plan> plans;  // by log_n
+  std::map<int, uint4*> loc_scaled;  // log_n -> (1/n) * loc[]
   unsigned long long launches = 0;
   std::string last_err;
 };
@@ -154,14 +155,43 @@ int transform(ntt384_ctx* ctx, void* d_data, int log_n, int batch, bool inverse,
   A.inverse = inverse ? 1 : 0;
   std::memcpy(A.c8, ctx->c8[inverse ? 1 : 0], sizeof(A.c8));
   A.batch_stride = 1ull << log_n;
-  if (inverse) un_to_limbs<W>(inv_pow2(ctx, log_n), A.scale);
+  A.scaled_round = -1;
+  const uint4* loc_scaled = nullptr;
+  if (inverse) {
+    un_to_limbs<W>(inv_pow2(ctx, log_n), A.scale);
+    if (plan->passes.back().nrounds >= 2) {
+      auto it = ctx->loc_scaled.find(log_n);
+      if (it == ctx->loc_scaled.end()) {
+        uint4* tab = nullptr;
+        const unsigned long long count = 1ull << ctx->loc_bits;
+        CTX_CUDA(cudaMalloc((void**)&tab, count * 4 * NL));
+        FeN<NL> c;
+        un_to_limbs<W>(inv_pow2(ctx, log_n), c.v);
+        table_scale_kernel_n<NL><<<(unsigned)((count + 127) / 128), 128, 0, stream>>>(tab, ctx->loc, count, ctx->fp, c);
+        ++ctx->launches;
+        CTX_CUDA(cudaGetLastError());
+        CTX_CUDA(cudaStreamSynchronize(stream));  // one-off: later calls may use other streams
+        it = ctx->loc_scaled.emplace(log_n, tab).first;
+      }
+      loc_scaled = it->second;
+    }
+  }
   const int kSlice = 65535;
   for (int b0 = 0; b0 < batch; b0 += kSlice) {
     const int nb = std::min(kSlice, batch - b0);
     uint4* p = (uint4*)d_data + (size_t)(NL / 4) * ((size_t)b0 << log_n);
     for (size_t i = 0; i < plan->passes.size(); ++i) {
       A.pd = plan->passes[i];
-      if (inverse && i + 1 == plan->passes.size()) A.pd.scale_out = 1;
+      A.scaled_round = -1;
+      A.loc_scaled = nullptr;
+      if (inverse && i + 1 == plan->passes.size()) {
+        if (loc_scaled) {
+          A.scaled_round = 0;  // 1/n folded into the first round's twiddles of the last pass
+          A.loc_scaled = loc_scaled;
+        } else {
+          A.pd.scale_out = 1;
+        }
+      }
       const int T = A.pd.T;
       const unsigned long long nblk = 1ull << A.pd.nblk_bits;
       if (nblk > 0x7fffffffull) return NTT256_ERR_ARG;
@@ -257,6 +287,7 @@ void ntt384_ctx_destroy(ntt384_ctx* ctx) {
   if (ctx->om_hi) cudaFree(ctx->om_hi);
   if (ctx->om_lo) cudaFree(ctx->om_lo);
   if (ctx->loc) cudaFree(ctx->loc);
+  for (auto& kv : ctx->loc_scaled) cudaFree(kv.second);
   delete ctx;
 }
 
@@ -265,7 +296,7 @@ int ntt384_ctx_set_tuning(ntt384_ctx* ctx, int tile_bits, int coalesce_bits) {
     return NTT256_ERR_ARG;
   ctx->tile_bits = tile_bits;
   ctx->coalesce_bits = coalesce_bits;
-  ctx->plans.clear();
+  ctx->plans.clear();  // loc_scaled tables depend on log_n only and stay valid
   return NTT256_OK;
 }
 

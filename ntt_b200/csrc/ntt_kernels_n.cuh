@@ -26,6 +26,10 @@ struct PassArgsN {
   u32 c8[3][NL];  // w_8^1..3 (or inverses), Montgomery form
   u32 scale[NL];  // 1/n, Montgomery form (pd.scale_out)
   unsigned long long batch_stride;
+  // inverse: round `scaled_round` of this pass reads loc_scaled = (1/n) * loc and multiplies every
+  // element (also the one whose twiddle is 1), which applies the 1/n without an extra product
+  int scaled_round;
+  const uint4* loc_scaled;
 };
 
 template <int NL>
@@ -72,7 +76,7 @@ NTT_DEV void bfly_n(u32* a, u32* b, const FieldParamsN<NL>& f) {
 
 // NB DIF stages on the top NB bits of the GB-bit register index + the round twiddle (cf. round_compute).
 template <int NL, int GB, int NB>
-NTT_DEV void round_compute_n(u32 (*x)[NL], const PassArgsN<NL>& A, bool last, u32 lam0, int sb, int lowp) {
+NTT_DEV void round_compute_n(u32 (*x)[NL], const PassArgsN<NL>& A, bool last, bool scaled, u32 lam0, int sb, int lowp) {
   const FieldParamsN<NL>& f = A.f;
 #pragma unroll
   for (int k = 0; k < NB; ++k) {
@@ -93,6 +97,7 @@ NTT_DEV void round_compute_n(u32 (*x)[NL], const PassArgsN<NL>& A, bool last, u3
   const u32 tl_mask = (1u << (pb - lowp)) - 1u;
   const u32 tl0 = (lam0 >> lowp) & tl_mask;
   const int ush = sb - lowp;
+  const uint4* loc_tab = scaled ? A.loc_scaled : A.loc;
 #pragma unroll
   for (int u = 0; u < (1 << GB); ++u) {
     const int uproc = u >> (GB - NB);
@@ -100,13 +105,13 @@ NTT_DEV void round_compute_n(u32 (*x)[NL], const PassArgsN<NL>& A, bool last, u3
 #pragma unroll
     for (int i = 0; i < NB; ++i) v |= ((uproc >> i) & 1) << (NB - 1 - i);
     const u32 rest = u & ((1 << (GB - NB)) - 1);
-    if (uproc != 0) {
+    if (scaled || uproc != 0) {
       const u32 tl = (tl0 | (rest << ush)) & tl_mask;
       u32 e = (tl * (u32)v) << sh;
       if (A.inverse) e = (0u - e);
       e &= (1u << A.loc_bits) - 1u;
       u32 w[NL];
-      ld_table_n<NL>(w, A.loc, e);
+      ld_table_n<NL>(w, loc_tab, e);
       mul_by_n<NL>(x[u], w, f);
     }
   }
@@ -162,10 +167,11 @@ NTT_DEV void ntt_pass_body_n(uint4* data, const PassArgsN<NL>& A, u32* smem) {
       }
     }
 
+    const bool scaled = (r == A.scaled_round);
     if (nb == 2) {
-      if constexpr (GB >= 2) round_compute_n<NL, GB, 2>(x, A, last, lam0, sb, lowp);
+      if constexpr (GB >= 2) round_compute_n<NL, GB, 2>(x, A, last, scaled, lam0, sb, lowp);
     } else if (nb == 1) {
-      round_compute_n<NL, GB, 1>(x, A, last, lam0, sb, lowp);
+      round_compute_n<NL, GB, 1>(x, A, last, scaled, lam0, sb, lowp);
     }
 
     if (!last) {
@@ -255,6 +261,21 @@ __global__ void twiddle_powers_kernel_n(uint4* __restrict__ out, const uint4* __
   }
   canonicalize_n<NL>(acc, f);
   st_el<NL>(out + (NL / 4) * i, acc);
+}
+
+// out[i] = c * in[i] (c a Montgomery-form constant): scaled copies of small tables.
+template <int NL>
+__global__ void table_scale_kernel_n(uint4* __restrict__ out, const uint4* __restrict__ in, unsigned long long count,
+                                     const __grid_constant__ FieldParamsN<NL> f, const __grid_constant__ FeN<NL> c) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u32 x[NL], t[NL];
+  ld_el<NL>(x, in + (NL / 4) * i);
+#pragma unroll
+  for (int k = 0; k < NL; ++k) t[k] = c.v[k];
+  mul_by_n<NL>(x, t, f);
+  canonicalize_n<NL>(x, f);
+  st_el<NL>(out + (NL / 4) * i, x);
 }
 
 // Element-wise product: mont_form = 1: out = a*b/R (Montgomery-form data in and out);
