@@ -1,8 +1,7 @@
 """384-bit containers (include/ntt384.h, SURVEY.md par. 8f row 4): the CUDA path through the C ABI
 against the Python-int oracle over BLS12-377 Fq (377 bits) -- bit-exact -- plus round trips and
-linearity at sizes the Python oracle does not reach.  The reference instantiates its templates at
-bits = 256 only, so parity here rests on the same algorithm statement (py_oracle.ntt_ref =
-big-num.cu:37-55) that is pinned on the 256-bit fields."""
+linearity at sizes the Python oracle does not reach, and the outputs of the reference's own GZKP
+driver instantiated at 512-bit containers over the same field (tests/golden/ref512_gpu_kat.json)."""
 import numpy as np
 import pytest
 
@@ -152,3 +151,49 @@ def test_large_sizes_closed_form_linearity_round_trip(env, log_n):
     for k in (0, 1, n // 3, n - 1):
         ia, ib, is_ = (sum(int(v) << (32 * i) for i, v in enumerate(t[k].cpu().numpy().view(np.uint32))) for t in (Ah, Bh, Sh))
         assert (ia + ib) % p == is_, k
+
+
+def test_library_matches_the_reference_gzkp_golden_vectors(env):
+    """tests/golden/ref512_gpu_kat.json: outputs of the reference's own NTT_GZKP (512-bit containers)
+    over BLS12-377 Fq on a B200; ntt384_forward must give the same 48-byte images."""
+    import hashlib
+    import json
+    import os
+
+    torch, ctx, (p, g) = env
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref512_gpu_kat.json")) as f:
+        kat = json.load(f)
+    for case in kat["cases"]:
+        n = 1 << case["log_n"]
+        if case["input"] == "iota":
+            vals = list(range(n))
+        else:
+            rng = np.random.default_rng(case["seed"])
+            vals = [int.from_bytes(rng.bytes(48), "little") % p for _ in range(n)]
+        got = _run(torch, ctx.forward, _to_limbs(vals), case["log_n"])
+        assert hashlib.sha256(got.tobytes()).hexdigest() == case["sha256"], (case["log_n"], case["input"])
+
+
+def test_library_against_the_reference_gzkp_driver_live(env):
+    """When oracle/_ref/libref512.so travelled to the box: fresh random inputs through the reference's
+    NTT_GZKP<16,512> and through ntt384_forward, compared as integers."""
+    import ctypes
+    import os
+
+    torch, ctx, (p, g) = env
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref512.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref512.so not present (built only where /root/reference exists)")
+    R = ctypes.CDLL(path)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    R.ref512_ntt_gzkp.argtypes = [u32p, ctypes.c_uint, u32p, u32p]
+    rng = np.random.default_rng()
+    pl = np.array([(p >> (32 * k)) & 0xFFFFFFFF for k in range(16)], dtype=np.uint32)
+    gl = np.array([(g >> (32 * k)) & 0xFFFFFFFF for k in range(16)], dtype=np.uint32)
+    for log_n in (5, 9, 13):
+        vals = [int.from_bytes(rng.bytes(48), "little") % p for _ in range(1 << log_n)]
+        a = np.zeros((1 << log_n, 16), dtype=np.uint32)
+        a[:, :12] = _to_limbs(vals)
+        assert R.ref512_ntt_gzkp(a.ctypes.data_as(u32p), log_n, pl.ctypes.data_as(u32p), gl.ctypes.data_as(u32p)) == 0
+        ours = _run(torch, ctx.forward, _to_limbs(vals), log_n)
+        assert not a[:, 12:].any() and np.array_equal(a[:, :12], ours), log_n

@@ -167,3 +167,30 @@ def test_oracle_matches_the_reference_gpu_drivers_on_the_big_fields(built):
             xi = [sum(int(x[i][k]) << (32 * k) for k in range(8)) for i in range(len(x))]
             want = po.ntt_ref(xi, F)
             assert [sum(int(got[i][k]) << (32 * k) for k in range(8)) for i in range(len(x))] == want
+
+
+def _ref512_vals(case, p):
+    n = 1 << case["log_n"]
+    if case["input"] == "iota":
+        return list(range(n))
+    rng = np.random.default_rng(case["seed"])
+    return [int.from_bytes(rng.bytes(48), "little") % p for _ in range(n)]
+
+
+def test_oracle_matches_the_reference_gzkp_driver_on_a_377_bit_field(built):
+    """tests/golden/ref512_gpu_kat.json: the reference's NTT_GZKP instantiated at 512-bit containers
+    (compiled unmodified, oracle/ref512_harness.cu) run on a B200 over BLS12-377 Fq.  The Python
+    oracle must reproduce the digests (sizes it reaches in seconds): pins the 384-bit path's oracle."""
+    kat = _load("ref512_gpu_kat.json")
+    F = po.BLS12_377_FQ
+    checked = 0
+    for case in kat["cases"]:
+        assert case["ours_equals_reference"]
+        if case["log_n"] > 10:
+            continue
+        got = po.ntt_ref(_ref512_vals(case, F.p), F)
+        img = b"".join(v.to_bytes(48, "little") for v in got)
+        assert hashlib.sha256(img).hexdigest() == case["sha256"], (case["log_n"], case["input"])
+        assert [hex(v) for v in got[:3]] == case["first"]
+        checked += 1
+    assert checked >= 8
