@@ -117,3 +117,15 @@ def test_product_does_not_import_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     src = f.read()
                 assert "oracle" not in src.replace("CPU oracle NTT()", ""), f"{fn} mentions the oracle"
+
+
+def test_host_field_arithmetic_cpp(built):
+    """tests/cpp/hostfield_test.cpp: the host-side constant derivation (R, R^2, -p^-1, powers,
+    inverses) of both widths -- the generic W-limb field equals the 256-bit one at W = 4 and satisfies
+    the field identities over BLS12-377 Fq at W = 6."""
+    import subprocess
+
+    d = os.path.join(ROOT, "tests", "cpp")
+    subprocess.check_call(["make", "-C", d, "hostfield_test"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([os.path.join(d, "hostfield_test")], capture_output=True, text=True)
+    assert out.returncode == 0 and "HOSTFIELD_OK" in out.stdout, out.stdout
