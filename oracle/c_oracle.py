@@ -95,6 +95,23 @@ def ntt(data: np.ndarray, p: int, g: int, inverse: bool = False, threads: int = 
     return out
 
 
+def ntt384(data: np.ndarray, p: int, g: int, inverse: bool = False, threads: int = 1) -> np.ndarray:
+    """Out-of-place wrapper around oracle_ntt384 (ntt_oracle_n.c, W = 6) on an [n, 12] uint32 array."""
+    out = np.ascontiguousarray(data, dtype=np.uint32).copy()
+    n = out.shape[0]
+    log_n = n.bit_length() - 1
+    assert n == 1 << log_n and out.shape[1] == 12
+    L = lib()
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    L.oracle_ntt384.argtypes = [u32p, ctypes.c_int, u32p, u32p, ctypes.c_int, ctypes.c_int]
+    pl = np.array([(p >> (32 * k)) & 0xFFFFFFFF for k in range(12)], dtype=np.uint32)
+    gl = np.array([(g >> (32 * k)) & 0xFFFFFFFF for k in range(12)], dtype=np.uint32)
+    rc = L.oracle_ntt384(_p(out), log_n, _p(pl), _p(gl), int(inverse), threads)
+    if rc:
+        raise ValueError(f"oracle_ntt384 rc={rc}")
+    return out
+
+
 def ntt_ssip(data: np.ndarray, p: int, g: int) -> np.ndarray:
     out = np.ascontiguousarray(data, dtype=np.uint32).copy()
     log_n = out.shape[0].bit_length() - 1

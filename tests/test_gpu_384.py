@@ -197,3 +197,23 @@ def test_library_against_the_reference_gzkp_driver_live(env):
         assert R.ref512_ntt_gzkp(a.ctypes.data_as(u32p), log_n, pl.ctypes.data_as(u32p), gl.ctypes.data_as(u32p)) == 0
         ours = _run(torch, ctx.forward, _to_limbs(vals), log_n)
         assert not a[:, 12:].any() and np.array_equal(a[:, :12], ours), log_n
+
+
+def test_full_c_oracle_2p18(env):
+    """Every output of a 2^18-point transform against the C oracle (oracle/ntt_oracle_n.c, pinned to the
+    reference's GZKP digests), forward and inverse, plus a batch of 8 x 2^15."""
+    from oracle import c_oracle as co
+
+    torch, ctx, (p, g) = env
+    rng = np.random.default_rng(2018)
+    log_n = 18
+    x = rng.integers(0, 1 << 32, size=(1 << log_n, 12), dtype=np.uint64).astype(np.uint32)
+    x[:, 11] &= 0x00FFFFFF  # below 2^376 < p
+    want = co.ntt384(x, p, g, threads=8)
+    got = _run(torch, ctx.forward, x, log_n)
+    assert np.array_equal(got, want)
+    assert np.array_equal(_run(torch, ctx.inverse, got, log_n), x)
+    n = 1 << 15
+    gotb = _run(torch, ctx.forward, x, 15, 8)
+    for b in range(8):
+        assert np.array_equal(gotb[b * n:(b + 1) * n], co.ntt384(x[b * n:(b + 1) * n], p, g, threads=8)), b

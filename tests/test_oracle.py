@@ -194,3 +194,32 @@ def test_oracle_matches_the_reference_gzkp_driver_on_a_377_bit_field(built):
         assert [hex(v) for v in got[:3]] == case["first"]
         checked += 1
     assert checked >= 8
+
+
+def _arr12(vals):
+    a = np.zeros((len(vals), 12), dtype=np.uint32)
+    for i, v in enumerate(vals):
+        for k in range(12):
+            a[i, k] = (v >> (32 * k)) & 0xFFFFFFFF
+    return a
+
+
+def test_c_oracle_384_equals_python_and_the_reference_gzkp_digests(built):
+    """oracle/ntt_oracle_n.c (W = 6): equal to py_oracle on random data (forward and inverse,
+    2^0 .. 2^10), and to EVERY digest of tests/golden/ref512_gpu_kat.json -- including the 2^12 and
+    2^14 cases the Python oracle is too slow for."""
+    import random
+
+    F = po.BLS12_377_FQ
+    rng = random.Random(384)
+    for log_n in range(0, 11):
+        vals = [rng.randrange(F.p) for _ in range(1 << log_n)]
+        fwd = co.ntt384(_arr12(vals), F.p, F.g, threads=1 + log_n % 3)
+        assert np.array_equal(fwd, _arr12(po.ntt_ref(vals, F))), log_n
+        inv = co.ntt384(_arr12(vals), F.p, F.g, inverse=True, threads=2)
+        assert np.array_equal(inv, _arr12(po.ntt_ref(vals, F, inverse=True))), log_n
+        assert np.array_equal(co.ntt384(fwd, F.p, F.g, inverse=True), _arr12(vals))
+    kat = _load("ref512_gpu_kat.json")
+    for case in kat["cases"]:
+        got = co.ntt384(_arr12(_ref512_vals(case, F.p)), F.p, F.g, threads=4)
+        assert hashlib.sha256(got.tobytes()).hexdigest() == case["sha256"], (case["log_n"], case["input"])
