@@ -38,6 +38,20 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _int_peak():
+    """32x32->64 multiply-accumulate rate of one B200 (T MAC/s): measured by scripts/microbench_issue.cu
+    (kernel k_wide_acc: IMAD.WIDE.U32 with a 64-bit accumulate; ncu shows the fmaheavy pipe, the only one
+    with an integer multiplier, ~95 % busy at 4 cycles per warp instruction) and committed in
+    profiles/r02_int_peak.json.  MEASURED_PEAKS.json has no integer figure."""
+    path = os.path.join(ROOT, "profiles", "r02_int_peak.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["wide_mac_T_per_s"]), "measured: profiles/r02_int_peak.json (" + d.get("how", "") + ")"
+    except Exception:
+        return 148 * 32 * 1.965e9 / 1e12, "nominal: 148 SMs x 32 IMAD.WIDE/clk x 1.965 GHz (profiles/r02_int_peak.json missing)"
+
+
 class ClockSampler:
     """SM clock and throttle reasons through NVML, sampled while the timed region's kernels run.
 
@@ -107,6 +121,9 @@ def synthetic_elements(n: int, p: int, seed: int):
     return x
 
 
+_CPU_INPUT: dict = {}
+
+
 def cpu_baseline(sample_log_n: int, threads: int, reps: int = 1):
     """Times the oracle port of the reference's CPU NTT (big-num.cu:37-55 restated over the
     256-bit field) on the host cores.  Returns (elements/s, seconds, description)."""
@@ -116,7 +133,9 @@ def cpu_baseline(sample_log_n: int, threads: int, reps: int = 1):
     from ntt_b200.api import FIELDS
 
     p, g = FIELDS[FIELD]
-    x = c_oracle.splitmix_elements(1 << sample_log_n, p, 0x4E5454 + 3)
+    x = _CPU_INPUT.get(sample_log_n)
+    if x is None:
+        x = _CPU_INPUT[sample_log_n] = c_oracle.splitmix_elements(1 << sample_log_n, p, 0x4E5454 + 3)
     best = None
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -129,7 +148,7 @@ def cpu_baseline(sample_log_n: int, threads: int, reps: int = 1):
 def run_reference(args):
     """--impl reference: the reference's CPU path.  The reference has no 256-bit CPU NTT (its
     NTT() is int64 over a 29-bit prime), so this arm times the oracle port -- the same algorithm
-    over BN254 Fr -- with every host thread, on a bounded sample (2^22 points per step), and also
+    over BN254 Fr -- with every host thread, on the full 2^24-point workload every step, and also
     reports the literal reference NTT() (oracle/_ref, int64) for continuity."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -137,7 +156,7 @@ def run_reference(args):
     from oracle import c_oracle
 
     threads = max(1, os.cpu_count() or 1)
-    sample_log_n = 22
+    sample_log_n = LOG_N  # the full workload: ~2 s per step on 16 cores, so K steps still end within minutes
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(sample_log_n, threads)
     t_total = 0.0
@@ -164,8 +183,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (256-bit modular integer)", "data": "synthetic",
-        "config": {"workload": f"forward NTT, {FIELD}, bounded sample 2^{sample_log_n} points per step "
-                               f"of the 2^{LOG_N} workload", "field": FIELD},
+        "config": {"workload": f"2^{LOG_N}-point forward NTT, {FIELD} (8x u32 limbs), in place, natural order in/out",
+                   "field": FIELD, "log_n": LOG_N, "sample": "the whole workload every step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"2^{sample_log_n}-point forward NTT per step, OpenMP over butterflies"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -251,12 +270,173 @@ def run_reference_gpu(args):
     print(json.dumps(line), flush=True)
 
 
+def _device_elements(torch, n: int, seed: int):
+    """n canonical elements made on the device (int32 limbs, top limb < 2^28 < p's top limb)."""
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed)
+    x = torch.randint(0, 1 << 31, (n, 8), dtype=torch.int32, device="cuda", generator=gen)
+    x[:, 7] &= 0x0FFFFFFF
+    return x.view(-1)
+
+
+def _timed(torch, dist, stream, step, steps, clk=None):
+    """Device time of `steps` calls of step(): barrier + synchronize on both sides, CUDA events on the
+    launching stream, max over ranks.  Returns ms in total."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    if clk is not None:
+        clk.poll_until(e1)  # the GPU is still inside the timed region: the host ran ahead of it
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms
+
+
+def _mgpu_parity(torch, dist, np, ctx, args, world, rank, p, g):
+    """Before anything is timed on N > 1 GPUs: a 2^20-point four-step transform through the same code
+    path (same exchange, same barrier), gathered on rank 0 and compared element by element with the
+    oracle (/root/reference/src/big-num.cu:446-467 checks every size it runs).  Returns a description."""
+    from ntt_b200 import dist as nd
+    from oracle import c_oracle
+
+    log_n = 20
+    shards = [synthetic_elements((1 << log_n) // world, p, 7000 + r) for r in range(world)] if rank == 0 else None
+    mine = synthetic_elements((1 << log_n) // world, p, 7000 + rank)
+    fs = nd.FourStep(ctx, log_n, world, rank, fused=not args.no_fused, barrier=args.barrier)
+    fs.load_shard(torch.from_numpy(mine.view(np.int32)).cuda().view(-1))
+    out = fs.forward().clone()
+    torch.cuda.synchronize()
+    gathered = [torch.empty_like(out) for _ in range(world)]
+    dist.all_gather(gathered, out)
+    ok = True
+    if rank == 0:
+        X = nd.gather_output([t.cpu().numpy().view(np.uint32).reshape(-1, 8) for t in gathered], log_n, world)
+        x = nd.gather_input_layout(shards, log_n, world)
+        ok = bool(np.array_equal(X, c_oracle.ntt(x, p, g, threads=max(1, os.cpu_count() or 1))))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    fs.close()
+    if not int(flag.item()):
+        raise AssertionError(f"bench: four-step 2^{log_n} over {world} GPUs differs from the oracle")
+    return f"2^{log_n} four-step over {world} ranks == oracle (all {1 << log_n} outputs)"
+
+
+def _mgpu_spot_check(torch, dist, np, fs, x_shard, world, rank, p, g, ks):
+    """Horner check of outputs X[k], k in ks, of the LOG_N-point distributed transform that fs has just
+    run on the shards made by synthetic_elements(seed 100 + rank)."""
+    from ntt_b200 import dist as nd
+    from oracle import c_oracle
+
+    n = 1 << LOG_N
+    out = fs.a if not fs.fused else (fs.a if fs._cur == 0 else fs.b)  # the buffer holding the result
+    vals = []
+    for k in ks:
+        owner, idx = nd.output_location(k, LOG_N, world, fs.log_r)
+        t = torch.zeros(8, dtype=torch.int32, device="cuda")
+        if rank == owner:
+            t.copy_(out.view(-1)[8 * idx: 8 * idx + 8])
+        dist.broadcast(t, owner)
+        vals.append(t.cpu().numpy().view(np.uint32))
+    if rank == 0:
+        x = nd.gather_input_layout([synthetic_elements(n // world, p, 0x4E5454 + 100 + r) for r in range(world)],
+                                   LOG_N, world, fs.log_r)
+        for k, v in zip(ks, vals):
+            have = sum(int(v[i]) << (32 * i) for i in range(8))
+            if c_oracle.dft_sample(x, p, g, k) != have:
+                raise AssertionError(f"bench: X[{k}] of the 2^{LOG_N} transform over {world} GPUs differs from the oracle")
+    dist.barrier()
+    return f"X[k] of the timed 2^{LOG_N} transform == Horner on the CPU for k in {list(ks)}"
+
+
+def _config3(torch, dist, np, ctx, args, world, rank, p, g, stream):
+    """BASELINE config 3: a batch of 256 independent 2^16-point transforms, sharded over the ranks with no
+    collective (ntt_b200.dist.shard_batch); transform 0 of every rank is compared with the oracle."""
+    from ntt_b200 import dist as nd
+    from oracle import c_oracle
+
+    batch, log_n = 256, 16
+    lo, hi = nd.shard_batch(batch, world, rank)
+    d = _device_elements(torch, (hi - lo) << log_n, 3000 + rank)
+    first = d[: 8 << log_n].cpu().numpy().view(np.uint32).reshape(-1, 8).copy()
+    ctx.forward(d, log_n, batch=hi - lo)
+    torch.cuda.synchronize()
+    got = d[: 8 << log_n].cpu().numpy().view(np.uint32).reshape(-1, 8)
+    if not np.array_equal(got, c_oracle.ntt(first, p, g, threads=4)):
+        raise AssertionError("bench: config 3 transform differs from the oracle")
+    for _ in range(2):
+        ctx.forward(d, log_n, batch=hi - lo)
+    steps = max(5, min(args.steps, 20))
+    ms = _timed(torch, dist, stream, lambda: ctx.forward(d, log_n, batch=hi - lo), steps) / steps
+    return {"workload": "256 x 2^16-point forward NTTs, bn254_fr, sharded %d per GPU, no collective" % (hi - lo),
+            "ms_per_step": ms, "value": (batch << log_n) / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "checked": "transform 0 of every rank == oracle"}
+
+
+def _config5(torch, dist, np, args, world, rank, local_rank, p, g, stream):
+    """BASELINE config 5: one 2^28-point transform (8 GiB) four-step over 8 GPUs.  Input x[j] = c*h^j (built on
+    the device from two small power tables), so sampled outputs are checked against the closed form."""
+    from ntt_b200 import dist as nd
+    from ntt_b200.api import Ntt256
+
+    log_n = 28
+    n = 1 << log_n
+    c, h = 0x1234567890ABCDEF1122334455667788 % p, 7
+    ctx = Ntt256(FIELD, max_log_n=log_n, device=local_rank)
+    fs = nd.FourStep(ctx, log_n, world, rank, fused=not args.no_fused, barrier=args.barrier)
+    col, row = nd.geometric_shard(c, h, p, log_n, world, rank, fs.log_r)
+    R, w = col.shape[0], row.shape[0]
+    a = torch.from_numpy(col.view(np.int32)).cuda().view(R, 1, 8).expand(R, w, 8).contiguous().view(-1)
+    b = torch.from_numpy(row.view(np.int32)).cuda().view(1, w, 8).expand(R, w, 8).contiguous().view(-1)
+    ctx.vec_mul(a, b, out=a)  # shard[j1][j2] = col[j1] * row[j2]
+    del b
+    fs.load_shard(a)
+    del a
+    torch.cuda.empty_cache()
+    fs.forward()
+    torch.cuda.synchronize()
+    out = fs.a if fs._cur == 0 else fs.b
+    bad = 0
+    for k in (0, 1, n // 2 + 7, n - 1, 123456789 % n, (rank * 0x9E3779B1 + 17) % n):
+        owner, idx = nd.output_location(k, log_n, world, fs.log_r)
+        if owner == rank:
+            v = out.view(-1)[8 * idx: 8 * idx + 8].cpu().numpy().view(np.uint32)
+            bad += int(sum(int(v[i]) << (32 * i) for i in range(8)) != nd.geometric_output(c, h, p, g, log_n, k))
+    t = torch.tensor([bad], device="cuda")
+    dist.all_reduce(t)
+    if int(t.item()):
+        raise AssertionError("bench: 2^28 transform over 8 GPUs differs from the closed form")
+    fs.forward()
+    steps = 3
+    ms = _timed(torch, dist, stream, fs.forward, steps) / steps
+    nvlink_bytes = 32.0 * (n / world) * (world - 1) / world  # sent (= received) per GPU per transform
+    fs.close()
+    ctx.close()
+    return {"workload": "2^28-point forward NTT, bn254_fr, four-step over 8 GPUs (1 GiB shard per GPU)",
+            "ms_per_step": ms, "value": n / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "nvlink_bytes_per_gpu_per_step": nvlink_bytes,
+            "nvlink_floor_ms": nvlink_bytes / 770e9 * 1e3,
+            "int_floor_ms": (n / 2) * log_n * MACS_PER_MODMUL / world / (_int_peak()[0] * 1e12) * 1e3,
+            "checked": "sampled X[k] == c(h^n-1)/(h w^k-1) on every rank"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
 
     from ntt_b200.api import FIELDS, Ntt256
-    from oracle import c_oracle  # checker only: the correctness spot-check and the cpu_baseline leg
+    from oracle import c_oracle  # checker only: the correctness checks and the cpu_baseline leg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -275,6 +455,7 @@ def run_ours(args):
     if args.tile_bits:
         ctx.set_tuning(args.tile_bits, args.coalesce_bits)
     stream = torch.cuda.current_stream()
+    checks = []
 
     if world == 1:
         x_host = synthetic_elements(n, p, 0x4E5454 + 3)
@@ -287,6 +468,7 @@ def run_ours(args):
     else:
         from ntt_b200.dist import FourStep
 
+        checks.append(_mgpu_parity(torch, dist, np, ctx, args, world, rank, p, g))
         fs = FourStep(ctx, LOG_N, world, rank, fused=not args.no_fused, log_r=(args.log_r or None),
                       barrier=args.barrier)
         x_shard = synthetic_elements(n // world, p, 0x4E5454 + 100 + rank)
@@ -295,39 +477,27 @@ def run_ours(args):
         def step():
             fs.forward()
 
-    # ---- correctness spot check before timing (one output via Horner on the CPU oracle)
+    # ---- correctness before timing: outputs of the workload itself by Horner on the CPU oracle
+    step()
+    torch.cuda.synchronize()
     if world == 1:
-        step()
-        torch.cuda.synchronize()
         got = d[: 8 * 4].cpu().numpy().view(np.uint32).reshape(-1, 8)
         for k in ((1, 3) if LOG_N <= 24 else (1,)):
             want = c_oracle.dft_sample(x_host, p, g, k)
             have = sum(int(got[k][i]) << (32 * i) for i in range(8))
             if want != have:
                 raise AssertionError(f"bench: X[{k}] differs from the oracle")
+        checks.append(f"X[1], X[3] of the timed 2^{LOG_N} transform == Horner on the CPU")
         d.copy_(torch.from_numpy(x_host.view(np.int32)))
+    elif LOG_N <= 24:
+        checks.append(_mgpu_spot_check(torch, dist, np, fs, x_shard, world, rank, p, g, (1, n // 2 + 7)))
 
     for _ in range(args.warmup):
         step()
     clk = ClockSampler(local_rank)  # NVML init takes a different time on every rank: before the barrier
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.launch_count
     barriers0 = fs._epoch if fs is not None else 0  # peer-barrier kernels (fused multi-GPU path)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()  # all ranks enter the timed region together (a late rank would be waited for
-        torch.cuda.synchronize()  # inside the first step's barrier and inflate everyone's time)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    clk.poll_until(e1)  # the GPU is still inside the timed region: the host ran ahead of it
-    torch.cuda.synchronize()
-    ms_total = e0.elapsed_time(e1)
-    if dist:
-        t = torch.tensor([ms_total], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = _timed(torch, dist, stream, step, args.steps, clk)
     launches = ctx.launch_count - launches0
     barrier_launches = (fs._epoch if fs is not None else 0) - barriers0
     ms_step = ms_total / args.steps
@@ -346,14 +516,24 @@ def run_ours(args):
         for _ in range(e2e_steps):
             ctx.forward_host(hin_np, LOG_N, out=hout_np)
         dt = (time.perf_counter() - t0) / e2e_steps
+        # the floor of any host-buffer call: the two PCIe copies alone (a single transform cannot overlap
+        # them: every output depends on every input)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            d.copy_(h_in, non_blocking=True)
+            h_out.copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+        floor = (time.perf_counter() - t0) / 2
         e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32,
-               "ms_per_step": dt * 1e3, "api": "ntt256_forward_host (pinned host buffers)"}
+               "ms_per_step": dt * 1e3, "floor_ms": floor * 1e3,
+               "floor": "H2D + D2H of the same pinned buffers with no transform (PCIe-bound)",
+               "api": "ntt256_forward_host (pinned host buffers, zero-copy first/last pass)"}
     else:
         # every rank: its shard from pinned host memory -> device, distributed transform, result
         # shard back to pinned host memory; max over ranks of the wall time per step
         h_in = torch.from_numpy(x_shard.view(np.int32)).pin_memory().view(-1)
         h_out = torch.empty_like(h_in).pin_memory()
-        src = fs.a if not fs.fused else (fs.a if fs._cur == 0 else fs.b)
 
         def e2e_step():
             cur = fs.a if not fs.fused else (fs.a if fs._cur == 0 else fs.b)
@@ -376,30 +556,55 @@ def run_ours(args):
         e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32,
                "ms_per_step": dt * 1e3, "api": "per-rank pinned shard -> FourStep.forward -> pinned shard (all ranks)"}
 
+    # ---- the other multi-GPU deliverables of BASELINE.json, as extra keys (every rank takes part)
+    extra = {}
+    if not args.no_extra_configs and LOG_N == 24:
+        try:
+            extra["config3"] = _config3(torch, dist, np, ctx, args, world, rank, p, g, stream)
+        except AssertionError:
+            raise
+        except Exception as e:  # an extra key must never cost the headline line
+            extra["config3"] = {"error": repr(e)[:200]}
+        if world == 8 and FIELD == "bn254_fr":
+            try:
+                if fs is not None:
+                    fs.close()
+                    fs = None
+                extra["config5"] = _config5(torch, dist, np, args, world, rank, local_rank, p, g, stream)
+            except AssertionError:
+                raise
+            except Exception as e:
+                extra["config5"] = {"error": repr(e)[:200]}
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (ntt_pass_kernel): all launches of a step are that kernel
-    hbm_peak, peak_src = _peaks()
-    passes = launches / args.steps / (1 if world == 1 else 1)
+    # ---- rooflines of the dominant kernel (ntt_pass_kernel): all launches of a step are that kernel
+    hbm_peak, hbm_src = _peaks()
+    int_peak, int_src = _int_peak()
+    passes = launches / args.steps
     launch_ms = ms_total / max(launches, 1)
     n_local = n // world
     alg_bytes_transform = 64.0 * n_local * -(-LOG_N // 12)  # 64 B/element per <=12-stage pass
     alg_bytes_launch = alg_bytes_transform / max(passes, 1)
-    achieved = alg_bytes_launch / (launch_ms / 1e3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
-    if os.path.exists(tpath):
-        try:
-            with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    hbm_achieved = alg_bytes_launch / (launch_ms / 1e3) / 1e9
+    traffic, traffic_src = None, None
+    if world == 1 and LOG_N == 24:
+        for name in ("r02_ncu_summary.json", "r01_ncu_summary.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath):
+                try:
+                    with open(tpath) as f:
+                        traffic = json.load(f).get("dram_bytes_per_launch")
+                    traffic_src = f"profiles/{name}: ncu --set full of this workload at N=1 (dram__bytes_read+write per launch); not re-measured by this run"
+                    break
+                except Exception:
+                    traffic = None
     modmuls = (n / 2) * LOG_N
-    int_peak_macs = 18.3e12  # measured plain IMAD.WIDE rate, profiles/r01_microbench_pipes.jsonl
-    int_achieved = modmuls * MACS_PER_MODMUL / (ms_step / 1e3) / world
+    macs_launch = modmuls * MACS_PER_MODMUL / world / max(passes, 1)
+    int_achieved = macs_launch / (launch_ms / 1e3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -409,19 +614,23 @@ def run_ours(args):
                                   + ("NCCL all-to-all" if args.no_fused else "peer stores fused into the butterfly kernel (NVLink), " + args.barrier + " barrier")),
                    "field": FIELD, "log_n": LOG_N, "passes_per_step": passes,
                    "l2_policy": "input 512 MiB > 126 MB L2, no flush needed",
-                   "binding_roofline": "int32-multiply pipe (see roofline_int); HBM is ~6x off"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "kernel": "ntt_pass_kernel", "launch_ms": launch_ms,
-                     "algorithmic_bytes_per_launch": alg_bytes_launch, "peak_source": peak_src},
-        "roofline_int": {"bound": "int32-mul", "achieved": int_achieved / 1e12, "peak": int_peak_macs / 1e12,
-                         "unit": "T wide-MAC/s", "frac": int_achieved / int_peak_macs,
-                         "work": "136 MACs x (n/2) log2 n modmuls (SURVEY 8d)",
-                         "peak_source": "measured plain IMAD.WIDE.U32 rate, profiles/r01_microbench_pipes.jsonl",
-                         "carry_chain_peak": 9.2, "frac_of_carry_chain_peak": int_achieved / 9.2e12,
-                         "note": "256-bit products need carry-predicate IMAD.WIDE forms, which run at half rate on "
-                                 "B200 (9.2 T/s): profiles/r01_microbench_notes.md"},
+                   "checked_before_timing": checks},
+        # the binding roofline: the 32x32->64 integer multiplier (fmaheavy pipe); HBM is ~6x off
+        "roofline": {"bound": "int32-mul", "achieved": int_achieved, "peak": int_peak, "unit": "T wide-MAC/s",
+                     "frac": int_achieved / int_peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": "ntt_pass_kernel", "launch_ms": launch_ms,
+                     "algorithmic_macs_per_launch": macs_launch,
+                     "work": "136 MACs x (n/2) log2 n modmuls (SURVEY 8d), whatever the multiplier really issues",
+                     "peak_source": int_src,
+                     "frac_of_r01_denominator": int_achieved / 18.3,
+                     "r01_denominator_note": "round 1 divided by 18.3 T/s, a figure its microbenchmark never measured "
+                                             "(ptxas had hoisted the product: the loop timed 64-bit adds); see BASELINE.md"},
+        "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": hbm_achieved / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes_launch,
+                         "peak_source": hbm_src},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches + barrier_launches),
     }
+    line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
         threads = max(1, os.cpu_count() or 1)
         v, secs = cpu_baseline(23, threads)
@@ -444,6 +653,7 @@ def main():
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--coalesce-bits", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config3 / config5 extra keys")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of fused peer stores")
     ap.add_argument("--barrier", choices=("flags", "nccl"), default="flags",
                     help="multi-GPU fused path: peer-memory flag barrier (default) or a one-element NCCL all-reduce")

@@ -83,6 +83,14 @@ int ntt256_ctx_set_small_transform_limit(ntt256_ctx* ctx, long long max_elements
  * for ntt256_forward/inverse[_batch]; 0 restores the automatic choice.  Tiles are limited to 2^11
  * elements below 3. */
 int ntt256_ctx_set_elements_per_thread(ntt256_ctx* ctx, int log2_elements);
+/* Twiddle representation of the pass kernels.  1 (the default whenever p < 2^254, e.g. BN254 Fr): tables
+ * hold 64-byte pairs (w, floor(w 2^256 / p)) and a twiddle product is a Shoup/Barrett multiplication
+ * (99 wide + 16 low 32-bit multiplies, csrc/field_shoup.cuh); 0 (the only choice for 255-bit moduli such as
+ * BLS12-381 Fr): 32-byte Montgomery-form entries and the Montgomery product (128 + 8).  Both give the same
+ * bits; switching rebuilds the tables (synchronises the device).  NTT256_ERR_FIELD if 1 is asked of a field
+ * with p >= 2^254. */
+int ntt256_ctx_set_twiddle_mode(ntt256_ctx* ctx, int shoup);
+int ntt256_ctx_get_twiddle_mode(const ntt256_ctx* ctx);
 
 /* Forward NTT of 2^log_n points, in place on device memory, natural order in and out.
  * == NTT_GZKP<8,256>(data, 1<<log_n, ..., prime, omega, B, G)  (big-num.cu:458). */

@@ -108,6 +108,14 @@ class Ntt256:
         """Force the pass kernel with 2^log2_elements (1..3) elements per thread; 0 = automatic."""
         self._check(self._L.ntt256_ctx_set_elements_per_thread(self._h, log2_elements))
 
+    def set_twiddle_mode(self, shoup: bool):
+        """True: (w, floor(w 2^256/p)) tables and Shoup products (fields with p < 2^254); False: Montgomery."""
+        self._check(self._L.ntt256_ctx_set_twiddle_mode(self._h, int(bool(shoup))))
+
+    @property
+    def twiddle_mode(self) -> str:
+        return "shoup" if self._L.ntt256_ctx_get_twiddle_mode(self._h) else "montgomery"
+
     def set_stream_twiddle_limit(self, max_bytes: int):
         """Largest streamed first-pass twiddle array built automatically (0: always two lookups)."""
         self._check(self._L.ntt256_ctx_set_stream_twiddle_limit(self._h, max_bytes))

@@ -51,7 +51,10 @@ struct ntt256_ctx {
   uint4* om_lo = nullptr;
   uint4* loc = nullptr;
   int hi_bits = 0, lo_bits = 0, loc_bits = 0;
-  u32 c8[2][3][8];   // [direction][k-1] = w_8^(+-k)
+  u32 c8[2][3][8];   // [direction][k-1] = w_8^(+-k), Montgomery form
+  u32 c8p[2][3][8];  // the same constants plain, and their Shoup companions (shoup contexts)
+  u32 c8q[2][3][8];
+  bool shoup = false;  // p < 2^254: twiddle tables hold (w, wq) pairs and the passes multiply with shoup_mul
   u32 w4[2][8];
   int tile_bits = 11;
   int coalesce_bits = 2;
@@ -109,9 +112,10 @@ U256 pow2k(const HostField& hf, U256 b, int k) {  // b^(2^k)
 
 void to_u32(const U256& a, u32 out[8]) { u256_to_limbs(a, out); }
 
-int build_power_table(ntt256_ctx* ctx, uint4** out, const U256& base_mont, int bits) {
+// shoup_entries: 64-byte (w, wq) entries for the pass kernels of a shoup context; else 32-byte Montgomery form.
+int build_power_table(ntt256_ctx* ctx, uint4** out, const U256& base_mont, int bits, bool shoup_entries = false) {
   const unsigned long long count = 1ull << bits;
-  CTX_CUDA(cudaMalloc((void**)out, count * 32));
+  CTX_CUDA(cudaMalloc((void**)out, count * (shoup_entries ? 64 : 32)));
   std::vector<u32> pw(8 * 64, 0);
   U256 b = base_mont;
   for (int k = 0; k < std::max(bits, 1); ++k) {
@@ -121,16 +125,38 @@ int build_power_table(ntt256_ctx* ctx, uint4** out, const U256& base_mont, int b
   uint4* d_pw = nullptr;
   CTX_CUDA(cudaMalloc((void**)&d_pw, pw.size() * 4));
   CTX_CUDA(cudaMemcpy(d_pw, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));
-  Fe one;
+  Fe one, pinv;
   to_u32(ctx->hf.one, one.v);
+  to_u32(ctx->hf.pinv, pinv.v);
   const int threads = 128;
   const unsigned blocks = (unsigned)((count + threads - 1) / threads);
-  twiddle_powers_kernel<<<blocks, threads>>>(*out, d_pw, bits, 0ull, count, ctx->fp, one);
+  twiddle_powers_kernel<<<blocks, threads>>>(*out, d_pw, bits, 0ull, count, ctx->fp, one, shoup_entries ? 1 : 0, pinv);
   ++ctx->launches;
   CTX_CUDA(cudaGetLastError());
   CTX_CUDA(cudaDeviceSynchronize());
   CTX_CUDA(cudaFree(d_pw));
   return NTT256_OK;
+}
+
+void free_twiddle_tables(ntt256_ctx* ctx) {
+  if (ctx->om_hi) cudaFree(ctx->om_hi);
+  if (ctx->om_lo) cudaFree(ctx->om_lo);
+  if (ctx->loc) cudaFree(ctx->loc);
+  ctx->om_hi = ctx->om_lo = ctx->loc = nullptr;
+  for (auto& kv : ctx->loc_scaled) cudaFree(kv.second);
+  ctx->loc_scaled.clear();
+  for (auto& kv : ctx->tw_streams) cudaFree(kv.second);
+  ctx->tw_streams.clear();
+}
+
+// The three w_N power tables of the pass kernels, in the context's twiddle representation.
+int build_twiddle_tables(ntt256_ctx* ctx) {
+  int rc = build_power_table(ctx, &ctx->om_hi, pow2k(ctx->hf, ctx->wN, ctx->lo_bits), ctx->hi_bits, ctx->shoup);
+  if (rc) return rc;
+  rc = build_power_table(ctx, &ctx->om_lo, ctx->wN, ctx->lo_bits, ctx->shoup);
+  if (rc) return rc;
+  return build_power_table(ctx, &ctx->loc, pow2k(ctx->hf, ctx->wN, ctx->max_log_n - ctx->loc_bits), ctx->loc_bits,
+                           ctx->shoup);
 }
 
 // Plan request of a whole transform (kind 0) or of one local step of the four-step
@@ -251,14 +277,23 @@ struct IoSpec {  // optional out-of-place ends of a plan (device-visible pointer
 };
 
 // The pass kernel for 2^group_bits elements per thread.
-void launch_pass(int group_bits, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const uint4* in,
-                 uint4* out, const PassArgs& A) {
-  if (group_bits == 3)
-    ntt_pass_kernel<<<grid, threads, smem, stream>>>(in, out, A);
-  else if (group_bits == 2)
-    ntt_pass4_kernel<<<grid, threads, smem, stream>>>(in, out, A);
-  else
-    ntt_pass2_kernel<<<grid, threads, smem, stream>>>(in, out, A);
+void launch_pass(bool shoup, int group_bits, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream,
+                 const uint4* in, uint4* out, const PassArgs& A) {
+  if (shoup) {
+    if (group_bits == 3)
+      ntt_pass_kernel<true><<<grid, threads, smem, stream>>>(in, out, A);
+    else if (group_bits == 2)
+      ntt_pass4_kernel<true><<<grid, threads, smem, stream>>>(in, out, A);
+    else
+      ntt_pass2_kernel<true><<<grid, threads, smem, stream>>>(in, out, A);
+  } else {
+    if (group_bits == 3)
+      ntt_pass_kernel<false><<<grid, threads, smem, stream>>>(in, out, A);
+    else if (group_bits == 2)
+      ntt_pass4_kernel<false><<<grid, threads, smem, stream>>>(in, out, A);
+    else
+      ntt_pass2_kernel<false><<<grid, threads, smem, stream>>>(in, out, A);
+  }
 }
 
 // (2^k)^-1 mod p in Montgomery form (a host inversion is ~10 us: computed once per k)
@@ -282,13 +317,25 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
   A.lo_bits = ctx->lo_bits;
   A.loc_bits = ctx->loc_bits;
   A.inverse = inverse ? 1 : 0;
-  std::memcpy(A.c8, ctx->c8[inverse ? 1 : 0], sizeof(A.c8));
+  const bool sh = ctx->shoup;
+  std::memcpy(A.c8, sh ? ctx->c8p[inverse ? 1 : 0] : ctx->c8[inverse ? 1 : 0], sizeof(A.c8));
+  if (sh) {
+    std::memcpy(A.c8q, ctx->c8q[inverse ? 1 : 0], sizeof(A.c8q));
+    to_u32(ctx->hf.r2, A.r2);
+    to_u32(ctx->hf.pinv, A.pinv);
+  }
   A.batch_stride = batch_stride;
   A.scaled_round = -1;
   const uint4* loc_scaled = nullptr;
   if (scale_log_n >= 0) {
     const U256& ninv = inv_pow2(ctx, scale_log_n);
-    to_u32(ninv, A.scale);
+    if (sh) {
+      const U256 plain = ctx->hf.from_mont(ninv);
+      to_u32(plain, A.scale);
+      to_u32(ctx->hf.shoup_companion(plain), A.scaleq);
+    } else {
+      to_u32(ninv, A.scale);
+    }
     if (plan.passes.back().nrounds >= 2) {
       // fold 1/n into the twiddle table of the last pass's first round (all 8 elements of that
       // round are multiplied, the trivial one by (1/n)*R instead of being skipped)
@@ -296,10 +343,13 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
       if (it == ctx->loc_scaled.end()) {
         uint4* tab = nullptr;
         const unsigned long long count = 1ull << ctx->loc_bits;
-        CTX_CUDA(cudaMalloc((void**)&tab, count * 32));
-        Fe c;
+        CTX_CUDA(cudaMalloc((void**)&tab, count * (sh ? 64 : 32)));
+        Fe c, r2, pinv;
         to_u32(ninv, c.v);
-        table_scale_kernel<<<(unsigned)((count + 127) / 128), 128, 0, stream>>>(tab, ctx->loc, count, ctx->fp, c);
+        to_u32(ctx->hf.r2, r2.v);
+        to_u32(ctx->hf.pinv, pinv.v);
+        table_scale_kernel<<<(unsigned)((count + 127) / 128), 128, 0, stream>>>(tab, ctx->loc, count, ctx->fp, c,
+                                                                               sh ? 1 : 0, r2, pinv);
         ++ctx->launches;
         CTX_CUDA(cudaGetLastError());
         CTX_CUDA(cudaStreamSynchronize(stream));  // one-off: later calls may use other streams
@@ -324,7 +374,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
     A.tw_stream = nullptr;
     A.tw_gen_out = nullptr;
     if (A.pd.has_tw && A.pd.tw_lshift < ctx->lo_bits && ctx->tw_stream_limit > 0) {
-      const size_t tbytes = (size_t)32 << (A.pd.T + A.pd.nblk_bits);
+      const size_t tbytes = (size_t)(sh ? 64 : 32) << (A.pd.T + A.pd.nblk_bits);
       if (tbytes <= ctx->tw_stream_limit) {
         auto tkey = std::make_tuple(plan.id, (int)i, inverse ? 1 : 0);
         auto ts = ctx->tw_streams.find(tkey);
@@ -334,10 +384,10 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
             PassArgs G = A;
             G.tw_gen_out = tab;
             G.peer_bits = 0;
-            to_u32(ctx->hf.one, G.one);
+            to_u32(sh ? u256_small(1) : ctx->hf.one, G.one);
             const int Tg = G.pd.T;
             dim3 ggrid((unsigned)(1ull << G.pd.nblk_bits), 1, 1);
-            launch_pass(plan.group_bits, ggrid, 1u << (Tg - plan.group_bits), (size_t)32 << Tg, stream,
+            launch_pass(sh, plan.group_bits, ggrid, 1u << (Tg - plan.group_bits), (size_t)32 << Tg, stream,
                         (const uint4*)d_data, (uint4*)d_data, G);
             ++ctx->launches;
             CTX_CUDA(cudaGetLastError());
@@ -367,7 +417,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
     // first pass may read from `src_first`, last pass may write to `dst_last` (host-mapped buffers)
     const uint4* pin = (i == 0 && io && io->src_first) ? (const uint4*)io->src_first : (const uint4*)d_data;
     uint4* pout = (i + 1 == plan.passes.size() && io && io->dst_last) ? (uint4*)io->dst_last : (uint4*)d_data;
-    launch_pass(GB, grid, threads, smem, stream, pin, pout, A);
+    launch_pass(sh, GB, grid, threads, smem, stream, pin, pout, A);
     ++ctx->launches;
     CTX_CUDA(cudaGetLastError());
   }
@@ -430,9 +480,16 @@ int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse,
   const int kSlice = 65535;
   for (int b0 = 0; b0 < batch; b0 += kSlice) {
     const int nb = std::min(kSlice, batch - b0);
-    char* p = (char*)d_data + ((size_t)b0 << log_n) * 32;
+    const size_t off = ((size_t)b0 << log_n) * 32;
+    char* p = (char*)d_data + off;
+    // out-of-place ends (zero-copy host buffers) follow the slice: same offset in every buffer
+    IoSpec io_slice;
+    if (io) {
+      io_slice.src_first = io->src_first ? (const char*)io->src_first + off : nullptr;
+      io_slice.dst_last = io->dst_last ? (char*)io->dst_last + off : nullptr;
+    }
     rc = run_plan(ctx, *plan, p, 1ull << log_n, nb, inverse, inverse ? log_n : -1, stream, nullptr,
-                  (io && batch <= kSlice) ? io : nullptr);
+                  io ? &io_slice : nullptr);
     if (rc) return rc;
   }
   return NTT256_OK;
@@ -623,7 +680,14 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
   U256 P2;
   u256_add(P2, P, P);
   u256_to_limbs(P2, ctx->fp.p2);
+  {
+    U256 pbar;
+    u256_sub(pbar, u256_small(0), P);  // 2^256 - p
+    u256_to_limbs(pbar, ctx->fp.pbar);
+  }
   ctx->fp.np0 = (u32)ctx->hf.np0;
+  // shoup_mul's remainder lies in [0, 3p): it must fit 256 bits (field_shoup.cuh)
+  ctx->shoup = u256_bitlen(P) <= 254;
   ctx->g_mont = ctx->hf.to_mont(G);
   ctx->wN = root_of_unity(ctx->hf, ctx->g_mont, max_log_n);
   ctx->wN_inv = ctx->hf.inv(ctx->wN);
@@ -660,6 +724,15 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
       std::memcpy(ctx->c8[1][1], ctx->w4[1], 32);
     }
   }
+  // plain copies and Shoup companions of the by-value constants
+  std::memset(ctx->c8p, 0, sizeof(ctx->c8p));
+  std::memset(ctx->c8q, 0, sizeof(ctx->c8q));
+  for (int d = 0; d < 2; ++d)
+    for (int k = 0; k < 3; ++k) {
+      const U256 plain = ctx->hf.from_mont(u256_from_limbs(ctx->c8[d][k]));
+      to_u32(plain, ctx->c8p[d][k]);
+      to_u32(ctx->hf.shoup_companion(plain), ctx->c8q[d][k]);
+    }
   int rc = NTT256_OK;
   auto fail = [&](int code) {
     ntt256_ctx_destroy(ctx);
@@ -672,16 +745,16 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) ctx->tw_stream_limit = total_b / 16;
   }
-  if (cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMaxTileBits) !=
+  if (cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMaxTileBits) !=
           cudaSuccess ||
-      cudaFuncSetAttribute(ntt_pass4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess ||
-      cudaFuncSetAttribute(ntt_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess)
+      cudaFuncSetAttribute(ntt_pass4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess ||
+      cudaFuncSetAttribute(ntt_pass2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess ||
+      cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMaxTileBits) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(ntt_pass4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess ||
+      cudaFuncSetAttribute(ntt_pass2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess)
     return fail(NTT256_ERR_CUDA);
-  rc = build_power_table(ctx, &ctx->om_hi, pow2k(ctx->hf, ctx->wN, ctx->lo_bits), ctx->hi_bits);
-  if (rc) return fail(rc);
-  rc = build_power_table(ctx, &ctx->om_lo, ctx->wN, ctx->lo_bits);
-  if (rc) return fail(rc);
-  rc = build_power_table(ctx, &ctx->loc, pow2k(ctx->hf, ctx->wN, max_log_n - ctx->loc_bits), ctx->loc_bits);
+  rc = build_twiddle_tables(ctx);
   if (rc) return fail(rc);
   *out = ctx;
   return NTT256_OK;
@@ -707,11 +780,7 @@ int ntt256_ctx_create_named(ntt256_ctx** out, int device, int field, int max_log
 void ntt256_ctx_destroy(ntt256_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->om_hi) cudaFree(ctx->om_hi);
-  if (ctx->om_lo) cudaFree(ctx->om_lo);
-  if (ctx->loc) cudaFree(ctx->loc);
-  for (auto& kv : ctx->loc_scaled) cudaFree(kv.second);
-  for (auto& kv : ctx->tw_streams) cudaFree(kv.second);
+  free_twiddle_tables(ctx);
   for (auto& c : ctx->cosets) {
     cudaFree(c.hi);
     cudaFree(c.lo);
@@ -1051,6 +1120,19 @@ int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes) {
   ctx->tw_streams.clear();
   return NTT256_OK;
 }
+
+int ntt256_ctx_set_twiddle_mode(ntt256_ctx* ctx, int shoup) {
+  if (!ctx || (shoup != 0 && shoup != 1)) return NTT256_ERR_ARG;
+  if (shoup && u256_bitlen(ctx->hf.p) > 254) return NTT256_ERR_FIELD;
+  if ((shoup != 0) == ctx->shoup) return NTT256_OK;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  CTX_CUDA(cudaDeviceSynchronize());
+  free_twiddle_tables(ctx);
+  ctx->shoup = shoup != 0;
+  return build_twiddle_tables(ctx);
+}
+
+int ntt256_ctx_get_twiddle_mode(const ntt256_ctx* ctx) { return ctx && ctx->shoup ? 1 : 0; }
 
 int ntt256_ctx_set_elements_per_thread(ntt256_ctx* ctx, int log2_elements) {
   if (!ctx || log2_elements < 0 || log2_elements > 3) return NTT256_ERR_ARG;

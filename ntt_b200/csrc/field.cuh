@@ -29,9 +29,10 @@ typedef uint64_t u64;
 // Field constants travel as a __grid_constant__ kernel parameter, i.e. they sit in
 // the constant bank and are consumed directly as IMAD/IADD3 c[][] operands.
 struct FieldParams {
-  u32 p[8];   // modulus
-  u32 p2[8];  // 2p (fits: p < 2^255)
-  u32 np0;    // -p^{-1} mod 2^32
+  u32 p[8];     // modulus
+  u32 p2[8];    // 2p (fits: p < 2^255)
+  u32 pbar[8];  // 2^256 - p (shoup_mul, field_shoup.cuh)
+  u32 np0;      // -p^{-1} mod 2^32
   u32 pad[3];
 };
 

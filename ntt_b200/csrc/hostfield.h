@@ -66,8 +66,23 @@ inline int u256_bitlen(const U256& a) {
   return 0;
 }
 
+// low 256 bits of a*b
+inline U256 u256_mul_lo(const U256& a, const U256& b) {
+  uint64_t t[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) {
+    unsigned __int128 c = 0;
+    for (int j = 0; i + j < 4; ++j) {
+      c += (unsigned __int128)a.w[i] * b.w[j] + t[i + j];
+      t[i + j] = (uint64_t)c;
+      c >>= 64;
+    }
+  }
+  return U256{{t[0], t[1], t[2], t[3]}};
+}
+
 struct HostField {
   U256 p, r2, one;
+  U256 pinv;  // p^-1 mod 2^256 (Shoup companions, field_shoup.cuh)
   uint64_t np0;
 
   void init(const U256& prime) {
@@ -75,6 +90,13 @@ struct HostField {
     uint64_t inv = 1;
     for (int i = 0; i < 6; ++i) inv *= 2 - p.w[0] * inv;
     np0 = 0 - inv;
+    // Newton: y <- y*(2 - p*y) doubles the number of correct low bits (64 -> 128 -> 256)
+    pinv = u256_small(inv);
+    for (int i = 0; i < 2; ++i) {
+      U256 t = u256_mul_lo(p, pinv), two_minus;
+      u256_sub(two_minus, u256_small(2), t);
+      pinv = u256_mul_lo(pinv, two_minus);
+    }
     U256 x = u256_small(1);
     for (int i = 0; i < 512; ++i) {
       x = add(x, x);
@@ -123,6 +145,12 @@ struct HostField {
     return (t[4] || !bw) ? d : r;
   }
   U256 to_mont(const U256& a) const { return mul(a, r2); }
+  // floor(w * 2^256 / p) for a plain canonical w: (w*2^256 - (w*2^256 mod p)) / p, exact, as a product with p^-1
+  U256 shoup_companion(const U256& w_plain) const {
+    U256 wm = to_mont(w_plain), neg;
+    u256_sub(neg, u256_small(0), wm);
+    return u256_mul_lo(neg, pinv);
+  }
   U256 from_mont(const U256& a) const { return mul(a, u256_small(1)); }
   U256 pow(const U256& base_mont, const U256& e) const {
     U256 acc = one, b = base_mont;

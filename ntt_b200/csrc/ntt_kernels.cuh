@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "field.cuh"
+#include "field_shoup.cuh"
 #include "kernel_common.cuh"
 #include "plan.h"
 
@@ -51,7 +52,14 @@ struct PassArgs {
   // on this path, the integer pipe none.  tw_gen_out != null: the launch only WRITES that array.
   const uint4* tw_stream;
   uint4* tw_gen_out;
-  u32 one[8];  // R mod p
+  u32 one[8];  // the field's 1 as the twiddle chain starts from it: R mod p (Montgomery tables) or 1 (Shoup tables)
+  // Shoup twiddles (kernels instantiated with SH = true; fields with p < 2^254, see field_shoup.cuh): every
+  // table entry is 64 bytes, the constant w (plain, canonical) followed by wq = floor(w * 2^256 / p), and the
+  // constants passed by value carry their companions too.
+  u32 c8q[3][8];
+  u32 scaleq[8];
+  u32 r2[8];    // R^2 mod p: plain -> Montgomery form (only to derive companions when a table is generated)
+  u32 pinv[8];  // p^-1 mod 2^256
 };
 
 // ---------------------------------------------------------------- element I/O
@@ -81,6 +89,64 @@ NTT_DEV void mul_by(u32* x, const u32* w, const FieldParams& f) {
   for (int k = 0; k < 8; ++k) x[k] = r[k];
 }
 
+// ---------------------------------------------------------------- twiddles in either representation
+// SH = false: 32-byte entries, w in Montgomery form, product = mont_mul (128 wide + 8 low multiplies).
+// SH = true : 64-byte entries (w, wq), product = shoup_mul (99 wide + 16 low multiplies).
+template <bool SH>
+NTT_DEV void ld_tw(u32* w, u32* q, const uint4* tab, u32 idx) {
+  if constexpr (SH) {
+    const uint4* e = tab + 4 * (size_t)idx;
+    const uint4 a = __ldg(e), b = __ldg(e + 1), c = __ldg(e + 2), d = __ldg(e + 3);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    q[0] = c.x; q[1] = c.y; q[2] = c.z; q[3] = c.w;
+    q[4] = d.x; q[5] = d.y; q[6] = d.z; q[7] = d.w;
+  } else {
+    ld_table(w, tab, idx);
+  }
+}
+template <bool SH>
+NTT_DEV void mul_tw(u32* x, const u32* w, const u32* q, const FieldParams& f) {
+  u32 r[8];
+  if constexpr (SH) shoup_mul(r, x, w, q, f); else mont_mul(r, w, x, f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = r[k];
+}
+
+// r = low 256 bits of a * b (table generation only)
+NTT_DEV void mul_lo256(u32* r, const u32* a, const u32* b) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    u32 carry = 0;
+#pragma unroll
+    for (int j = 0; j + i < 8; ++j) {
+      const u64 t = (u64)a[i] * b[j] + r[i + j] + carry;
+      r[i + j] = (u32)t;
+      carry = (u32)(t >> 32);
+    }
+  }
+}
+// wq = floor(w * 2^256 / p) from wm = w * 2^256 mod p (canonical; it is the Montgomery form of w):
+// w * 2^256 - wm is an exact multiple of p, so the quotient is (-wm) * p^-1 modulo 2^256.
+NTT_DEV void shoup_companion(u32* wq, const u32* wm, const u32* pinv) {
+  u32 neg[8], zero[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) zero[k] = 0;
+  (void)sub256(neg, zero, wm);
+  mul_lo256(wq, neg, pinv);
+}
+// 64-byte Shoup entry (w, wq) from a plain canonical w: wm = w * R via one Montgomery product with R^2.
+NTT_DEV void st_shoup_entry(uint4* dst, const u32* w, const u32* r2, const u32* pinv, const FieldParams& f) {
+  u32 wm[8], wq[8];
+  mont_mul(wm, r2, w, f);
+  canonicalize(wm, f);
+  shoup_companion(wq, wm, pinv);
+  st_global_256(dst, w);
+  st_global_256(dst + 2, wq);
+}
+
 // DIF butterfly: (a, b) <- (a + b, a - b)
 NTT_DEV void bfly(u32* a, u32* b, const FieldParams& f) {
   u32 s[8], d[8];
@@ -96,7 +162,7 @@ NTT_DEV void bfly(u32* a, u32* b, const FieldParams& f) {
 // NB DIF stages on the top NB bits of the GB-bit register index, with the constant twiddles of
 // the 2^NB-point sub-transform (powers of w_8), followed -- unless this is the last round of the
 // pass -- by the round twiddle w_{2^m}^(tau_lo * v) from the table.
-template <int GB, int NB>
+template <int GB, int NB, bool SH>
 NTT_DEV void round_compute(u32 (*x)[8], const PassArgs& A, const FieldParams& f, bool last, bool scaled, u32 lam0,
                            int sb, int lowp) {
 #pragma unroll
@@ -108,7 +174,7 @@ NTT_DEV void round_compute(u32 (*x)[8], const PassArgs& A, const FieldParams& f,
       bfly(x[u], x[u | (1 << bit)], f);
       const int t = (u >> (GB - NB)) & ((1 << (NB - 1 - k)) - 1);  // lower processed bits of u
       const int e8 = t << (3 - (NB - k));                           // twiddle as a power of w_8
-      if (e8) mul_by(x[u | (1 << bit)], A.c8[e8 - 1], f);
+      if (e8) mul_tw<SH>(x[u | (1 << bit)], A.c8[e8 - 1], A.c8q[e8 - 1], f);
     }
   }
   if (last || NB == 0) return;
@@ -132,9 +198,9 @@ NTT_DEV void round_compute(u32 (*x)[8], const PassArgs& A, const FieldParams& f,
       u32 e = (tl * (u32)v) << sh;
       if (A.inverse) e = (0u - e);
       e &= (1u << A.loc_bits) - 1u;
-      u32 w[8];
-      ld_table(w, loc_tab, e);
-      mul_by(x[u], w, f);
+      u32 w[8], wq[8];
+      ld_tw<SH>(w, wq, loc_tab, e);
+      mul_tw<SH>(x[u], w, wq, f);
     }
   }
 }
@@ -142,7 +208,7 @@ NTT_DEV void round_compute(u32 (*x)[8], const PassArgs& A, const FieldParams& f,
 // One pass.  GB = log2(elements per thread): 3 is the throughput configuration (radix-8 rounds,
 // 64 data registers); 2 halves the serial work per thread and doubles the number of warps, which
 // is what small, latency-bound transforms need.
-template <int GB>
+template <int GB, bool SH>
 NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs& A, u32* smem) {
   constexpr int NE = 1 << GB;
   const PassDesc& pd = A.pd;
@@ -205,11 +271,11 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
     if (!gen) {
       const bool scaled = (r == A.scaled_round);
       if (nb == 3) {
-        if constexpr (GB >= 3) round_compute<GB, 3>(x, A, f, last, scaled, lam0, sb, lowp);
+        if constexpr (GB >= 3) round_compute<GB, 3, SH>(x, A, f, last, scaled, lam0, sb, lowp);
       } else if (nb == 2) {
-        if constexpr (GB >= 2) round_compute<GB, 2>(x, A, f, last, scaled, lam0, sb, lowp);
+        if constexpr (GB >= 2) round_compute<GB, 2, SH>(x, A, f, last, scaled, lam0, sb, lowp);
       } else if (nb == 1) {
-        round_compute<GB, 1>(x, A, f, last, scaled, lam0, sb, lowp);
+        round_compute<GB, 1, SH>(x, A, f, last, scaled, lam0, sb, lowp);
       }
     }
 
@@ -235,9 +301,9 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
           u32 off = (u32)base_t + g0;
 #pragma unroll
           for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
-          u32 w[8];
-          ld_table(w, A.tw_stream, off);
-          mul_by(x[u], w, f);
+          u32 w[8], wq[8];
+          ld_tw<SH>(w, wq, A.tw_stream, off);
+          mul_tw<SH>(x[u], w, wq, f);
         }
       } else if (pd.has_tw) {
         u32 jl0 = jlow_blk;
@@ -258,18 +324,18 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
           u32 e = (jl * khi) << pd.tw_lshift;
           if (A.inverse) e = (0u - e);
           e &= nmask;
-          u32 w[8];
-          ld_table(w, A.om_hi, e >> A.lo_bits);
-          mul_by(x[u], w, f);
+          u32 w[8], wq[8];
+          ld_tw<SH>(w, wq, A.om_hi, e >> A.lo_bits);
+          mul_tw<SH>(x[u], w, wq, f);
           if (two) {
-            ld_table(w, A.om_lo, e & lomask);
-            mul_by(x[u], w, f);
+            ld_tw<SH>(w, wq, A.om_lo, e & lomask);
+            mul_tw<SH>(x[u], w, wq, f);
           }
         }
       }
       if (pd.scale_out) {
 #pragma unroll
-        for (int u = 0; u < NE; ++u) mul_by(x[u], A.scale, f);
+        for (int u = 0; u < NE; ++u) mul_tw<SH>(x[u], A.scale, A.scaleq, f);
       }
       if (pd.is_final) {
 #pragma unroll
@@ -285,7 +351,10 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
 #pragma unroll
           for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
           canonicalize(x[u], f);
-          st_global_256(A.tw_gen_out + 2 * (size_t)off, x[u]);
+          if constexpr (SH)
+            st_shoup_entry(A.tw_gen_out + 4 * (size_t)off, x[u], A.r2, A.pinv, f);
+          else
+            st_global_256(A.tw_gen_out + 2 * (size_t)off, x[u]);
         }
       } else if (A.peer_bits == 0) {
 #pragma unroll
@@ -315,26 +384,29 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
 // data_in == data_out: in place (the normal case).  They differ when the first / last pass of
 // a host-buffer transform reads / writes pinned host memory directly (zero-copy over PCIe, so the
 // transfer overlaps the pass instead of preceding / following it).
+template <bool SH>
 __global__ void __launch_bounds__(512, 1)
 ntt_pass_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
   extern __shared__ u32 smem[];
-  ntt_pass_body<3>(data_in, data_out, A, smem);
+  ntt_pass_body<3, SH>(data_in, data_out, A, smem);
 }
 
 // Four elements per thread (radix-4 rounds): twice the warps, half the serial work per thread --
 // used for small transforms, which are latency-bound with eight elements per thread.
+template <bool SH>
 __global__ void __launch_bounds__(512, 1)
 ntt_pass4_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
   extern __shared__ u32 smem[];
-  ntt_pass_body<2>(data_in, data_out, A, smem);
+  ntt_pass_body<2, SH>(data_in, data_out, A, smem);
 }
 
 // Two elements per thread (radix-2 rounds): the lowest-latency shape, for transforms so small that
 // even the four-element kernel leaves most of the chip idle.
+template <bool SH>
 __global__ void __launch_bounds__(1024, 1)
 ntt_pass2_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
   extern __shared__ u32 smem[];
-  ntt_pass_body<1>(data_in, data_out, A, smem);
+  ntt_pass_body<1, SH>(data_in, data_out, A, smem);
 }
 
 // Transforms of 2 or 4 points: one thread per transform, exact radix-2 DIF + bit reversal.
@@ -380,9 +452,11 @@ __global__ void ntt_tiny_kernel(uint4* __restrict__ data, const __grid_constant_
 
 // out[i] = prod over set bits k of i of pw[k]   (pw[k] = w^(2^k) in Montgomery form), i.e. w^i.
 // `first` offsets the exponent: out[i] = w^(first + i).
+// shoup != 0: 64-byte entries (w plain, wq) instead of the 32-byte Montgomery form.
 __global__ void twiddle_powers_kernel(uint4* __restrict__ out, const uint4* __restrict__ pw, int nbits,
                                       unsigned long long first, unsigned long long count,
-                                      const __grid_constant__ FieldParams f, const __grid_constant__ Fe one) {
+                                      const __grid_constant__ FieldParams f, const __grid_constant__ Fe one,
+                                      int shoup, const __grid_constant__ Fe pinv) {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const unsigned long long e = first + i;
@@ -397,7 +471,16 @@ __global__ void twiddle_powers_kernel(uint4* __restrict__ out, const uint4* __re
     }
   }
   canonicalize(acc, f);
-  st_global_256(out + 2 * i, acc);
+  if (!shoup) {
+    st_global_256(out + 2 * i, acc);
+    return;
+  }
+  u32 w[8], wq[8], unit[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  mont_mul(w, acc, unit, f);  // (w R) * 1 / R = w; acc is canonical, a valid left operand
+  canonicalize(w, f);
+  shoup_companion(wq, acc, pinv.v);
+  st_global_256(out + 4 * i, w);
+  st_global_256(out + 4 * i + 2, wq);
 }
 
 // ---------------------------------------------------------------- element-wise companions
@@ -478,15 +561,21 @@ __global__ void coset_scale_direct_kernel(uint4* __restrict__ data, unsigned lon
 }
 
 // out[i] = c * in[i]  (c Montgomery-form constant): scaled copies of small tables.
+// shoup != 0: both tables hold 64-byte (w, wq) entries; c stays a Montgomery-form constant, and
+// montmul(c R, w) = c*w is already the plain product.
 __global__ void table_scale_kernel(uint4* __restrict__ out, const uint4* __restrict__ in, unsigned long long count,
-                                   const __grid_constant__ FieldParams f, const __grid_constant__ Fe c) {
+                                   const __grid_constant__ FieldParams f, const __grid_constant__ Fe c, int shoup,
+                                   const __grid_constant__ Fe r2, const __grid_constant__ Fe pinv) {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   u32 x[8];
-  ld_global_256(x, in + 2 * i);
+  ld_global_256(x, in + (shoup ? 4 : 2) * i);
   mul_by(x, c.v, f);
   canonicalize(x, f);
-  st_global_256(out + 2 * i, x);
+  if (shoup)
+    st_shoup_entry(out + 4 * i, x, r2.v, pinv.v, f);
+  else
+    st_global_256(out + 2 * i, x);
 }
 
 }  // namespace ntt256

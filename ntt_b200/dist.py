@@ -64,6 +64,44 @@ def gather_input_layout(shards: list[np.ndarray], log_n: int, world: int, log_r:
     return np.ascontiguousarray(np.concatenate([s.reshape(R, C // world, 8) for s in shards], axis=1)).reshape(-1, 8)
 
 
+def output_location(k: int, log_n: int, world: int, log_r: int | None = None) -> tuple[int, int]:
+    """(rank, element index inside that rank's output shard) of X[k] after FourStep.forward()."""
+    log_r = default_log_r(log_n) if log_r is None else log_r
+    R, C = 1 << log_r, 1 << (log_n - log_r)
+    k1, k2 = k % R, k // R
+    return k1 // (R // world), ((k2 % world) * (R // world) + k1 % (R // world)) * (C // world) + k2 // world
+
+
+def geometric_shard(c: int, h: int, p: int, log_n: int, world: int, rank: int, log_r: int | None = None):
+    """Factors of the input x[j] = c*h^j restricted to `rank`'s input shard (column block of the R x C
+    view): the shard is the outer product col[j1] * row[j2_local] with col[j1] = c*h^(rank*w)*(h^C)^j1 and
+    row[j2] = h^j2.  Returned as two uint32 arrays [R, 8] and [C/P, 8] (Python integers, no transform):
+    a dense input whose transform has the closed form X[k] = c*(h^n - 1)/(h*w_n^k - 1), which is what lets a
+    2^28-point distributed transform be checked exactly without a second one."""
+    log_r = default_log_r(log_n) if log_r is None else log_r
+    R, C = 1 << log_r, 1 << (log_n - log_r)
+    w = C // world
+
+    def powers(first, ratio, count):
+        out = np.empty((count, 8), dtype=np.uint32)
+        v = first % p
+        for i in range(count):
+            for l in range(8):
+                out[i, l] = (v >> (32 * l)) & 0xFFFFFFFF
+            v = v * ratio % p
+        return out
+
+    return powers(c * pow(h, rank * w, p), pow(h, C, p), R), powers(1, h, w)
+
+
+def geometric_output(c: int, h: int, p: int, g: int, log_n: int, k: int) -> int:
+    """X[k] of the transform of x[j] = c*h^j:  c*(h^n - 1)/(h*w_n^k - 1) mod p  (h*w_n^k != 1)."""
+    n = 1 << log_n
+    wk = pow(pow(g, (p - 1) >> log_n, p), k, p)
+    den = (h * wk - 1) % p
+    return c * (pow(h, n, p) - 1) * pow(den, p - 2, p) % p
+
+
 def shard_batch(batch: int, world: int, rank: int) -> tuple[int, int]:
     """Transforms [lo, hi) of a batch handled by `rank` (independent units, no collective)."""
     per = (batch + world - 1) // world

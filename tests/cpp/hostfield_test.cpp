@@ -67,6 +67,28 @@ int main() {
   UIntN<6> w = q.pow(gm, un_shr(pm1, 46));
   for (int i = 0; i < 45; ++i) w = q.mul(w, w);
   check(un_cmp(w, minus1) == 0, "W=6 w_{2^46}^(2^45) == -1");
+  // Shoup companions (field_shoup.cuh): p * pinv == 1 mod 2^256, and wq = floor(w 2^256 / p), i.e.
+  // wq*p <= w*2^256 < (wq+1)*p, checked through the low halves: w*2^256 - wq*p == (w*2^256 mod p) < p.
+  {
+    U256 one256 = u256_mul_lo(h.p, h.pinv);
+    check(one256.w[0] == 1 && !one256.w[1] && !one256.w[2] && !one256.w[3], "p * pinv == 1 (mod 2^256)");
+    bool ok = true;
+    uint64_t s2 = 0x9e3779b97f4a7c15ull;
+    for (int it = 0; it < 200 && ok; ++it) {
+      U256 w;
+      for (int i = 0; i < 4; ++i) { s2 ^= s2 << 13; s2 ^= s2 >> 7; s2 ^= s2 << 17; w.w[i] = s2; }
+      w.w[3] &= 0x0fffffffffffffffull;  // < p
+      if (it == 0) w = u256_small(0);
+      if (it == 1) w = u256_small(1);
+      if (it == 2) u256_sub(w, h.p, u256_small(1));
+      U256 wq = h.shoup_companion(w);
+      // low 256 bits of (0 - wq*p) must equal w*2^256 mod p = to_mont(w), which is < p
+      U256 lo = u256_mul_lo(wq, h.p), rem;
+      u256_sub(rem, u256_small(0), lo);
+      ok = ok && u256_cmp(rem, h.to_mont(w)) == 0 && u256_cmp(rem, h.p) < 0;
+    }
+    check(ok, "shoup_companion(w) == floor(w 2^256 / p) on 200 values incl. 0, 1, p-1");
+  }
   std::printf("%s\n", fails ? "HOSTFIELD_FAIL" : "HOSTFIELD_OK");
   return fails ? 1 : 0;
 }

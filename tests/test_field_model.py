@@ -157,3 +157,73 @@ def test_lazy_add_sub_window():
         if a < b:
             diff = (diff + 2 * p) & ((1 << 256) - 1)
         assert diff < 2 * p and diff % p == (a - b) % p
+
+
+# --------------------------------------------------------------------------- shoup_mul (field_shoup.cuh)
+def _shoup():
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "gen_shoup_mul.py")
+    spec = importlib.util.spec_from_file_location("gen_shoup_mul", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_shoup_mul_header_is_what_the_generator_emits():
+    """ntt_b200/csrc/field_shoup.cuh is generated; the instruction list it was emitted from is the model
+    the tests below execute, so the committed header must be the generator's current output."""
+    import os
+
+    g = _shoup()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "ntt_b200", "csrc", "field_shoup.cuh")) as f:
+        assert f.read() == g.emit_cuda()
+
+
+def test_shoup_mul_multiply_counts():
+    g = _shoup()
+    pr, _ = g._PROG
+    wide = sum(1 for o in pr.ops if o[0].startswith("madc.hi"))
+    low = sum(1 for o in pr.ops if o[0] in ("mad.lo", "madc.lo"))
+    assert (wide, low) == (99, 16)  # against 128 + 8 of the Montgomery product
+
+
+@pytest.mark.parametrize("p", [po.BN254_FR.p, po.REF29.p, (1 << 254) - 127 * 2 + 1])
+def test_shoup_mul_model_is_exact_and_never_loses_a_carry(p):
+    """r = x*w mod p with r < 2p for every x < 2^256 and w < p, the uncorrected remainder below 3p, and no
+    instruction without a carry-out ever overflows except where the generator drops the carry on purpose
+    (the interpreter raises OverflowError otherwise)."""
+    g = _shoup()
+    if p % 2 == 0:
+        p += 1
+    rng = random.Random(20262)
+    worst = 0.0
+    specials_x = [0, 1, p - 1, p, 2 * p - 1, 2 * p, 3 * p, (1 << 256) - 1, (1 << 256) - p, 1 << 255, (1 << 224) - 1]
+    specials_w = [0, 1, 2, p - 1, p - 2, p // 2, p // 2 + 1, (p - 1) // 3]
+    cases = [(x, w) for x in specials_x for w in specials_w]
+    for i in range(6000):
+        kind = i % 4
+        x = (rng.randrange(1 << 256), rng.randrange(2 * p), (1 << 256) - 1 - rng.randrange(1 << 64),
+             rng.randrange(1 << 256) | (M32 << 224))[kind]
+        cases.append((x % (1 << 256), rng.randrange(p)))
+    for x, w in cases:
+        r, r0, _ = g.shoup_mul_model(x, w, p)
+        assert r % p == (x * w) % p
+        assert r < 2 * p and r0 < 3 * p
+        worst = max(worst, r0 / p)
+    assert worst < 3.0
+
+
+def test_shoup_quotient_is_at_most_one_below_the_true_floor():
+    g = _shoup()
+    p = po.BN254_FR.p
+    rng = random.Random(7)
+    for _ in range(2000):
+        x, w = rng.randrange(1 << 256), rng.randrange(p)
+        wq = (w << 256) // p
+        _, r0, _ = g.shoup_mul_model(x, w, p)
+        q = (x * w - r0) // p
+        assert (x * w - r0) % p == 0
+        assert ((x * wq) >> 256) - q in (0, 1)

@@ -220,13 +220,79 @@ def test_large_transform_properties(torch_cuda, ctxs, field, log_n):
 
 
 def test_full_oracle_2p22(torch_cuda, ctxs):
-    """Largest size the multi-threaded oracle finishes in seconds: full bit-exact comparison."""
+    """Full bit-exact comparison at 2^22 (a three-pass plan; 2^24 below is the four-pass one)."""
     from ntt_b200.api import FIELDS
     from oracle import c_oracle as co
 
     p, g = FIELDS["bn254_fr"]
     x = co.splitmix_elements(1 << 22, p, 99)
     assert np.array_equal(_gpu_forward(torch_cuda, ctxs("bn254_fr", 24), x, 22), co.ntt(x, p, g, threads=16))
+
+
+@pytest.mark.parametrize("field", ["bn254_fr", "bls12_381_fr"])
+def test_config4_full_2p24_bit_exact(torch_cuda, ctxs, field):
+    """The headline size, every element: the reference's own harness compares all 2^24 outputs with its
+    CPU NTT (/root/reference/src/big-num.cu:446-467); so does this test, forward and inverse, against
+    the multi-threaded C oracle (a few seconds on the box's host cores)."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    p, g = FIELDS[field]
+    n = 1 << 24
+    x = co.splitmix_elements(n, p, 0x4E5454 + 24)
+    threads = max(1, min(co.max_threads(), os.cpu_count() or 1))
+    want = co.ntt(x, p, g, threads=threads)
+    got = _gpu_forward(torch_cuda, ctxs(field, 24), x, 24)
+    assert np.array_equal(got, want)
+    assert np.array_equal(_gpu_forward(torch_cuda, ctxs(field, 24), want, 24, inverse=True), x)
+
+
+def test_shoup_and_montgomery_twiddles_give_the_same_bits(torch_cuda):
+    """BN254 Fr (p < 2^254) runs on (w, floor(w 2^256/p)) tables and Shoup products by default; the
+    Montgomery path (the only one for BLS12-381 Fr) must produce identical bytes: every plan shape, forward
+    and inverse (1/n folded into a scaled round table), batches, streamed and two-lookup pass twiddles, the
+    coset entry points.  A 255-bit modulus refuses the Shoup mode."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from ntt_b200.lib import ERR_FIELD, Ntt256Error
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = Ntt256("bn254_fr", max_log_n=22)
+    assert ctx.twiddle_mode == "shoup"
+    cases = [(3, 5), (7, 3), (12, 2), (16, 1), (19, 1), (21, 1)]
+    data = {c: co.splitmix_elements(c[1] << c[0], p, 600 + c[0]) for c in cases}
+    results = {}
+    for mode in (True, False, True):
+        ctx.set_twiddle_mode(mode)
+        assert ctx.twiddle_mode == ("shoup" if mode else "montgomery")
+        for limit in (1 << 40, 0):
+            ctx.set_stream_twiddle_limit(limit)
+            for (log_n, batch), x in data.items():
+                X = _gpu_forward(torch, ctx, x, log_n, batch=batch)
+                key = (log_n, batch)
+                if key not in results:
+                    n = 1 << log_n
+                    for b in range(batch):
+                        assert np.array_equal(X[b * n:(b + 1) * n], co.ntt(x[b * n:(b + 1) * n], p, g, threads=8)), key
+                    results[key] = X
+                assert np.array_equal(X, results[key]), (mode, limit, key)
+                assert np.array_equal(_gpu_forward(torch, ctx, X, log_n, batch=batch, inverse=True), x), (mode, limit, key)
+        d = torch.from_numpy(data[(16, 1)].view(np.int32).copy()).cuda()
+        ctx.coset_forward(d, 16, 7)
+        torch.cuda.synchronize()
+        got = d.cpu().numpy().copy()
+        assert np.array_equal(results.setdefault("coset", got), got), mode
+        ctx.coset_inverse(d, 16, 7)
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 8), data[(16, 1)])
+    ctx.close()
+    bls = Ntt256("bls12_381_fr", max_log_n=12)
+    assert bls.twiddle_mode == "montgomery"
+    with pytest.raises(Ntt256Error) as e:
+        bls.set_twiddle_mode(True)
+    assert e.value.status == ERR_FIELD
+    bls.close()
 
 
 # --------------------------------------------------------------------------- edge cases
@@ -528,6 +594,31 @@ def test_zero_copy_host_buffers(torch_cuda, ctxs):
         assert np.array_equal(buf.reshape(-1, 8), got)
         ctx.inverse_host(buf, log_n, batch=batch, out=buf)
         assert np.array_equal(buf.reshape(-1, 8), x)
+
+
+def test_zero_copy_host_buffers_with_more_transforms_than_one_grid(torch_cuda, ctxs):
+    """Batches above 65535 transforms are issued in slices (grid.y limit); the pinned zero-copy ends must
+    follow every slice (round-1 advisor finding: they were dropped and the call returned uninitialised
+    staging memory with status OK)."""
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = ctxs("bn254_fr", 24)
+    log_n, batch = 3, 70000
+    x = co.splitmix_elements(batch << log_n, p, 4321)
+    h_in = torch.from_numpy(x.view(np.int32).copy()).pin_memory()
+    h_out = torch.zeros_like(h_in).pin_memory()
+    got = ctx.forward_host(h_in.numpy().view(np.uint32), log_n, batch=batch, out=h_out.numpy().view(np.uint32)).reshape(-1, 8)
+    n = 1 << log_n
+    for b in (0, 1, 65534, 65535, 65536, 69999):
+        assert np.array_equal(got[b * n:(b + 1) * n], co.ntt(x[b * n:(b + 1) * n], p, g)), b
+    # the whole batch against the device-buffer entry point
+    assert np.array_equal(got, _gpu_forward(torch, ctx, x, log_n, batch=batch))
+    buf = h_out.numpy().view(np.uint32)
+    ctx.inverse_host(buf, log_n, batch=batch, out=buf)
+    assert np.array_equal(buf.reshape(-1, 8), x)
 
 
 def test_cpp_program_mirroring_the_reference_main(torch_cuda):
