@@ -498,8 +498,10 @@ def run_ours(args):
     launches0 = ctx.launch_count
     barriers0 = fs._epoch if fs is not None else 0  # peer-barrier kernels (fused multi-GPU path)
     ms_total = _timed(torch, dist, stream, step, args.steps, clk)
+    if fs is not None:
+        fs.check()  # no rank-synchronisation wait timed out
     launches = ctx.launch_count - launches0
-    barrier_launches = (fs._epoch if fs is not None else 0) - barriers0
+    barrier_launches = ((fs._epoch if fs is not None else 0) - barriers0) if args.barrier == "flags" else 0
     ms_step = ms_total / args.steps
     value = n / (ms_step / 1e3)
 
@@ -655,8 +657,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the config3 / config5 extra keys")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of fused peer stores")
-    ap.add_argument("--barrier", choices=("flags", "nccl"), default="flags",
-                    help="multi-GPU fused path: peer-memory flag barrier (default) or a one-element NCCL all-reduce")
+    ap.add_argument("--barrier", choices=("kernel", "flags", "nccl"), default="kernel",
+                    help="multi-GPU fused path: synchronisation folded into the pass kernels (default), a one-warp "
+                         "peer-memory barrier kernel, or a one-element NCCL all-reduce")
     ap.add_argument("--log-r", type=int, default=0, help="multi-GPU: rows = 2^log_r of the four-step view (0: automatic)")
     ap.add_argument("--field", default="bn254_fr", choices=["bn254_fr", "bls12_381_fr"])
     ap.add_argument("--log-n", type=int, default=24, help="transform size (default: the BASELINE metric's 2^24)")

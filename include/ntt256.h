@@ -191,10 +191,22 @@ int ntt256_ipc_free(int device, void* d_ptr);
  * `epoch` in every peer's buffer (after a system-scope fence, so the peer stores of the kernels
  * before it on the stream are visible first) and waits until every peer has published an epoch
  * >= `epoch` here.  Epochs must increase by one per call, identically on every rank.  A peer that
- * does not arrive within ~5 s traps the kernel (the stream then reports an error) instead of
- * hanging the GPU.  nranks <= 8. */
+ * does not arrive within the timeout (default 60 s, ntt256_set_peer_barrier_timeout) makes the waiter
+ * record the epoch in its flag buffer and give up -- no trap, the context and the IPC mappings stay
+ * usable; ntt256_peer_sync_status reports it after a synchronisation.  nranks <= 8. */
 int ntt256_peer_barrier(int device, void* const* flag_bufs, int nranks, int rank, unsigned long long epoch,
                         ntt256_stream stream);
+int ntt256_set_peer_barrier_timeout(double seconds);
+/* NTT256_OK if no waiter of this rank's flag buffer ever timed out; else NTT256_ERR_CUDA and the epoch it
+ * was waiting for in *timed_out_epoch (the results of that transform are invalid).  Synchronous. */
+int ntt256_peer_sync_status(int device, const void* flag_buf, unsigned long long* timed_out_epoch);
+/* The same synchronisation folded INTO the four-step kernels, no barrier launch at all: once a context is
+ * armed with every rank's flag buffer, the last pass of ntt256_fourstep[_inverse]_step1_peer ends by
+ * publishing a new epoch from its last CTA (after system-scope fences behind the peer stores), and the first
+ * pass of the following ntt256_fourstep[_inverse]_step2 begins with every CTA waiting for all ranks' epochs.
+ * Calls must alternate step1_peer / step2 identically on every rank.  flag_bufs == NULL or nranks <= 1
+ * disarms.  timeout_s <= 0 keeps the current timeout (default 60 s). */
+int ntt256_ctx_set_peer_sync(ntt256_ctx* ctx, void* const* flag_bufs, int nranks, int rank, double timeout_s);
 /* Lets kernels running on `device` store into memory of `peer_device` (NVLink peer access);
  * needed once per peer before ntt256_fourstep_step1_peer.  Already-enabled is not an error. */
 int ntt256_enable_peer_access(int device, int peer_device);

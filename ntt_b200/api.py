@@ -116,6 +116,15 @@ class Ntt256:
     def twiddle_mode(self) -> str:
         return "shoup" if self._L.ntt256_ctx_get_twiddle_mode(self._h) else "montgomery"
 
+    def set_peer_sync(self, flag_ptrs=None, rank: int = 0, timeout_s: float = 0.0):
+        """Arm (flag_ptrs = every rank's flag buffer as mapped here) or disarm (None) the rank
+        synchronisation folded into the four-step kernels (ntt256_ctx_set_peer_sync)."""
+        if flag_ptrs is None:
+            self._check(self._L.ntt256_ctx_set_peer_sync(self._h, None, 0, 0, 0.0))
+        else:
+            arr = (ctypes.c_void_p * len(flag_ptrs))(*[int(v) for v in flag_ptrs])
+            self._check(self._L.ntt256_ctx_set_peer_sync(self._h, arr, len(flag_ptrs), rank, float(timeout_s)))
+
     def set_stream_twiddle_limit(self, max_bytes: int):
         """Largest streamed first-pass twiddle array built automatically (0: always two lookups)."""
         self._check(self._L.ntt256_ctx_set_stream_twiddle_limit(self._h, max_bytes))

@@ -83,6 +83,12 @@ struct ntt256_ctx {
   std::map<PlanKey, Plan> plans;
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
+  // rank synchronisation folded into the four-step passes (ntt256_ctx_set_peer_sync)
+  unsigned long long sync_flags[8] = {};
+  int sync_nranks = 0, sync_rank = 0;
+  unsigned long long sync_epoch = 0;
+  unsigned long long sync_timeout_ns = 60ull * 1000000000ull;
+  unsigned int* sync_counter = nullptr;
   unsigned long long launches = 0;
   std::string last_err;
 };
@@ -305,8 +311,10 @@ const U256& inv_pow2(ntt256_ctx* ctx, int k) {
   return ctx->ninv[k];
 }
 
+// sync: 0 none; 1 the first pass waits for every rank's epoch; 2 the last pass publishes this rank's epoch
 int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long batch_stride, int batch, bool inverse,
-             int scale_log_n, cudaStream_t stream, const PeerSpec* peer = nullptr, const IoSpec* io = nullptr) {
+             int scale_log_n, cudaStream_t stream, const PeerSpec* peer = nullptr, const IoSpec* io = nullptr,
+             int sync = 0) {
   PassArgs A;
   std::memset(&A, 0, sizeof(A));
   A.f = ctx->fp;
@@ -406,6 +414,19 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
       A.peer_bits = peer->bits;
       A.peer_shift = peer->shift;
       A.peer_rank = peer->rank;
+    }
+    A.sync_mode = 0;
+    if (sync && ctx->sync_nranks > 1) {
+      if ((sync & 1) && i == 0) A.sync_mode |= 1;
+      if ((sync & 2) && i + 1 == plan.passes.size()) A.sync_mode |= 2;
+      if (A.sync_mode) {
+        std::memcpy(A.sync_flags, ctx->sync_flags, sizeof(A.sync_flags));
+        A.sync_epoch = ctx->sync_epoch;
+        A.sync_timeout_ns = ctx->sync_timeout_ns;
+        A.sync_counter = ctx->sync_counter;
+        A.sync_nranks = ctx->sync_nranks;
+        A.sync_rank = ctx->sync_rank;
+      }
     }
     const int T = A.pd.T;
     const int GB = plan.group_bits;
@@ -795,6 +816,7 @@ void ntt256_ctx_destroy(ntt256_ctx* ctx) {
     if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
   }
   if (ctx->d_stage) cudaFree(ctx->d_stage);
+  if (ctx->sync_counter) cudaFree(ctx->sync_counter);
   delete ctx;
 }
 
@@ -901,6 +923,9 @@ static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log
   // step 2 does not depend on the rank (no foreign time bits remain)
   int rc = get_plan(ctx, PlanKey{kind, log_n, log_r, log_p, first_step ? rank : 0}, &plan);
   if (rc) return rc;
+  // ranks armed with ntt256_ctx_set_peer_sync: step 1 with peer stores ends by publishing a new epoch,
+  // step 2 begins by waiting for it (from every rank)
+  const bool armed = ctx->sync_nranks == (1 << log_p) && log_p > 0;
   if (peer_recv && log_p > 0) {
     if (log_p > 3) return NTT256_ERR_ARG;
     PeerSpec ps;
@@ -908,9 +933,11 @@ static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log
     ps.bits = log_p;
     ps.shift = log_n - 2 * log_p;  // local index bits below the destination-rank field
     ps.rank = rank;
-    return run_plan(ctx, *plan, d_shard, 0, 1, inverse, scale_log_n, stream, &ps, io);
+    if (armed) ++ctx->sync_epoch;
+    return run_plan(ctx, *plan, d_shard, 0, 1, inverse, scale_log_n, stream, &ps, io, armed ? 2 : 0);
   }
-  return run_plan(ctx, *plan, d_shard, 0, 1, inverse, scale_log_n, stream, nullptr, io);
+  return run_plan(ctx, *plan, d_shard, 0, 1, inverse, scale_log_n, stream, nullptr, io,
+                  (armed && !first_step) ? 1 : 0);
 }
 
 int ntt256_fourstep_inverse_step1(ntt256_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
@@ -1121,6 +1148,30 @@ int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes) {
   return NTT256_OK;
 }
 
+int ntt256_ctx_set_peer_sync(ntt256_ctx* ctx, void* const* flag_bufs, int nranks, int rank, double timeout_s) {
+  if (!ctx) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  if (!flag_bufs || nranks <= 1) {  // disarm
+    ctx->sync_nranks = 0;
+    ctx->sync_epoch = 0;
+    return NTT256_OK;
+  }
+  if (nranks > 8 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return NTT256_ERR_ARG;
+  for (int r = 0; r < nranks; ++r) {
+    if (!flag_bufs[r]) return NTT256_ERR_ARG;
+    ctx->sync_flags[r] = (unsigned long long)flag_bufs[r];
+  }
+  if (!ctx->sync_counter) {
+    CTX_CUDA(cudaMalloc((void**)&ctx->sync_counter, sizeof(unsigned int)));
+    CTX_CUDA(cudaMemset(ctx->sync_counter, 0, sizeof(unsigned int)));
+  }
+  ctx->sync_nranks = nranks;
+  ctx->sync_rank = rank;
+  ctx->sync_epoch = 0;
+  if (timeout_s > 0) ctx->sync_timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  return NTT256_OK;
+}
+
 int ntt256_ctx_set_twiddle_mode(ntt256_ctx* ctx, int shoup) {
   if (!ctx || (shoup != 0 && shoup != 1)) return NTT256_ERR_ARG;
   if (shoup && u256_bitlen(ctx->hf.p) > 254) return NTT256_ERR_FIELD;
@@ -1147,9 +1198,11 @@ int ntt256_ctx_set_small_transform_limit(ntt256_ctx* ctx, long long max_elements
 }
 
 namespace {
+unsigned long long g_barrier_timeout_ns = 60ull * 1000000000ull;
 struct PeerBarrierArgs {
   unsigned long long flags[8];  // every rank's flag buffer, as mapped in this process
   unsigned long long epoch;
+  unsigned long long timeout_ns;
   int nranks, rank;
 };
 
@@ -1157,16 +1210,19 @@ struct PeerBarrierArgs {
 __global__ void peer_barrier_kernel(const __grid_constant__ PeerBarrierArgs A) {
   const int r = threadIdx.x;
   if (r >= A.nranks) return;
-  constexpr int kSlotBase = 256 / 8;  // flags start at byte 256 (the first words carry the IPC check stamp)
+  constexpr int kSlotBase = kSyncSlotBase;  // flags start at byte 256 (the first words carry the IPC check stamp)
   __threadfence_system();
   volatile unsigned long long* theirs = (volatile unsigned long long*)A.flags[r] + kSlotBase + A.rank;
   *theirs = A.epoch;
   volatile unsigned long long* mine = (volatile unsigned long long*)A.flags[A.rank] + kSlotBase + r;
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const unsigned long long t0 = global_timer_ns();
   while (*mine < A.epoch) {
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 5000000000ull) __trap();  // a peer died: fail loudly rather than hang the GPU
+    if (global_timer_ns() - t0 > A.timeout_ns) {
+      // a peer died or is very late: leave a mark the host can read (ntt256_peer_sync_status) and stop
+      // waiting -- no trap, the context and its IPC mappings stay usable
+      ((volatile unsigned long long*)A.flags[A.rank])[kSyncErrSlot] = A.epoch;
+      break;
+    }
   }
   __threadfence_system();
 }
@@ -1183,10 +1239,27 @@ int ntt256_peer_barrier(int device, void* const* flag_bufs, int nranks, int rank
     A.flags[r] = (unsigned long long)flag_bufs[r];
   }
   A.epoch = epoch;
+  A.timeout_ns = g_barrier_timeout_ns;
   A.nranks = nranks;
   A.rank = rank;
   peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(A);
   return cudaGetLastError() == cudaSuccess ? NTT256_OK : NTT256_ERR_CUDA;
+}
+
+int ntt256_set_peer_barrier_timeout(double seconds) {
+  if (!(seconds > 0)) return NTT256_ERR_ARG;
+  g_barrier_timeout_ns = (unsigned long long)(seconds * 1e9);
+  return NTT256_OK;
+}
+
+int ntt256_peer_sync_status(int device, const void* flag_buf, unsigned long long* timed_out_epoch) {
+  if (!flag_buf || !timed_out_epoch) return NTT256_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return NTT256_ERR_CUDA;
+  unsigned long long v = 0;
+  if (cudaMemcpy(&v, (const char*)flag_buf + 8 * kSyncErrSlot, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return NTT256_ERR_CUDA;
+  *timed_out_epoch = v;
+  return v ? NTT256_ERR_CUDA : NTT256_OK;
 }
 
 int ntt256_enable_peer_access(int device, int peer_device) {

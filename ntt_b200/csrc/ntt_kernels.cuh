@@ -60,7 +60,26 @@ struct PassArgs {
   u32 scaleq[8];
   u32 r2[8];    // R^2 mod p: plain -> Montgomery form (only to derive companions when a table is generated)
   u32 pinv[8];  // p^-1 mod 2^256
+  // Rank synchronisation folded into the passes (multi-GPU four-step, one process per GPU).  sync_mode bit 1
+  // (arrive, last pass of step 1): when the grid's last CTA has finished its peer stores it publishes
+  // sync_epoch in every rank's flag buffer.  Bit 0 (wait, first pass of step 2): every CTA first waits
+  // until all ranks' epochs have arrived in the local flag buffer.  No separate barrier kernel, no
+  // collective; the step-2 kernel is already resident while the last peer stores land.
+  unsigned long long sync_flags[8];   // flag buffer of every rank, as mapped in this process
+  unsigned long long sync_epoch;
+  unsigned long long sync_timeout_ns;
+  unsigned int* sync_counter;         // CTA arrival counter of this context (device memory, zero between uses)
+  int sync_mode, sync_nranks, sync_rank;
 };
+
+constexpr int kSyncSlotBase = 256 / 8;  // epochs start at byte 256 of a flag buffer (u64 slots, one per source rank)
+constexpr int kSyncErrSlot = 128 / 8;   // a waiter that timed out leaves the epoch it was waiting for here
+
+NTT_DEV unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ---------------------------------------------------------------- element I/O
 NTT_DEV void ld_global_256(u32* v, const uint4* p) {
@@ -232,6 +251,22 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
   const bool gen = (A.tw_gen_out != nullptr);
   const int lowp = T - d;  // lowest process bit
 
+  if (A.sync_mode & 1) {
+    // every rank's step 1 (and its peer stores into this rank's memory) must be complete
+    if (tid < (u32)A.sync_nranks) {
+      volatile unsigned long long* flags = (volatile unsigned long long*)A.sync_flags[A.sync_rank];
+      const unsigned long long t0 = global_timer_ns();
+      while (flags[kSyncSlotBase + tid] < A.sync_epoch) {
+        if (global_timer_ns() - t0 > A.sync_timeout_ns) {  // a peer died: record it, do not hang the GPU
+          flags[kSyncErrSlot] = A.sync_epoch;
+          break;
+        }
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+  }
+
   for (int r = gen ? pd.nrounds - 1 : 0; r < pd.nrounds; ++r) {
     const int sb = pd.round_sb[r];
     const int nb = pd.round_nb[r];
@@ -376,6 +411,21 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
           uint4* dst = reinterpret_cast<uint4*>(A.peer[off >> A.peer_shift]) + 2 * (size_t)(mine | (off & lowmask));
           st_global_256(dst, x[u]);
         }
+      }
+    }
+  }
+  if (A.sync_mode & 2) {
+    // this CTA's stores (peer memory included) are visible system-wide before it counts as arrived;
+    // the last CTA of the grid tells every rank
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int total = gridDim.x * gridDim.y;
+      if (atomicAdd(A.sync_counter, 1u) == total - 1u) {
+        *A.sync_counter = 0u;
+        __threadfence_system();
+        for (int r = 0; r < A.sync_nranks; ++r)
+          ((volatile unsigned long long*)A.sync_flags[r])[kSyncSlotBase + A.sync_rank] = A.sync_epoch;
       }
     }
   }

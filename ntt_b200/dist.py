@@ -123,10 +123,14 @@ class FourStep:
     fused=True : the exchange is the store phase of step 1's last kernel -- every output element
                  goes straight into the destination rank's receive buffer over NVLink
                  (peer-mapped memory shared through CUDA IPC); only a barrier separates the steps.
+    barrier    : how the fused path separates the steps.  "kernel" (default): no barrier launch at all --
+                 step 1's last kernel publishes an epoch from its last CTA, step 2's first kernel starts
+                 with every CTA waiting for all ranks' epochs (ntt256_ctx_set_peer_sync); "flags": the
+                 one-warp barrier kernel ntt256_peer_barrier; "nccl": a one-element all-reduce.
     """
 
     def __init__(self, ctx, log_n: int, world: int, rank: int, log_r: int | None = None, group=None,
-                 fused: bool = False, barrier: str = "flags"):
+                 fused: bool = False, barrier: str = "kernel"):
         self.ctx, self.log_n, self.world, self.rank, self.group = ctx, log_n, world, rank, group
         self.log_p = _log2(world)
         self.log_r = default_log_r(log_n) if log_r is None else log_r
@@ -135,8 +139,8 @@ class FourStep:
         self.fused = bool(fused) and world > 1
         # how the fused path separates step 1 (peer stores) from step 2: "flags" = the library's
         # peer-memory barrier kernel (ntt256_peer_barrier), "nccl" = a one-element all-reduce
-        if barrier not in ("flags", "nccl"):
-            raise ValueError("barrier must be 'flags' or 'nccl'")
+        if barrier not in ("kernel", "flags", "nccl"):
+            raise ValueError("barrier must be 'kernel', 'flags' or 'nccl'")
         self.barrier = barrier
         self._epoch = 0
         self.a = None
@@ -225,6 +229,8 @@ class FourStep:
 
         self._peers = ptrs[:2]
         self._flag_ptrs = (ctypes.c_void_p * self.world)(*ptrs[2])
+        if self.barrier == "kernel":
+            self.ctx.set_peer_sync(ptrs[2], self.rank)
         self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", self._dev))
         self._cur = 0  # which buffer holds the input
         dist.barrier(group=self.group)
@@ -232,7 +238,9 @@ class FourStep:
     def _step_barrier(self):
         """Every rank's step-1 kernel (and its peer stores) is complete before any rank's step 2
         starts; stream-ordered, the host does not block."""
-        if self.barrier == "flags":
+        if self.barrier == "kernel":
+            self._epoch += 1  # published and awaited inside the pass kernels: nothing to launch
+        elif self.barrier == "flags":
             import torch
 
             from .lib import Ntt256Error, lib
@@ -248,6 +256,19 @@ class FourStep:
             # a 1-element all-reduce completes on a rank only after every rank's NCCL kernel has
             # started, i.e. after every rank's step-1 kernel has finished
             dist.all_reduce(self._flag, group=self.group)
+
+    def check(self):
+        """After a synchronisation: raises if a rank-synchronisation wait of this rank ever timed out
+        (a peer died or was more than the timeout late), i.e. if a result may be built on missing data."""
+        import ctypes
+
+        from .lib import lib
+
+        if not self.fused or self._peers is None:
+            return
+        e = ctypes.c_ulonglong(0)
+        if lib().ntt256_peer_sync_status(self._dev, self._f.data_ptr(), ctypes.byref(e)):
+            raise RuntimeError(f"rank {self.rank}: peer synchronisation timed out waiting for epoch {e.value}")
 
     def _peek(self, ptr):
         import torch
@@ -265,6 +286,8 @@ class FourStep:
 
         if self.fused and self._peers is not None:
             torch.cuda.synchronize()
+            if self.barrier == "kernel":
+                self.ctx.set_peer_sync(None)
             try:
                 import torch.distributed as dist
 

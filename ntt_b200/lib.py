@@ -22,6 +22,7 @@ EXPORTS = [
     "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2", "ntt256_fourstep_step1_peer", "ntt256_enable_peer_access",
     "ntt256_fourstep_inverse_step1", "ntt256_fourstep_inverse_step1_peer", "ntt256_fourstep_inverse_step2",
     "ntt256_ipc_alloc", "ntt256_ipc_open", "ntt256_ipc_close", "ntt256_ipc_free", "ntt256_peer_barrier",
+    "ntt256_set_peer_barrier_timeout", "ntt256_peer_sync_status", "ntt256_ctx_set_peer_sync",
     "ntt256_mgpu_create", "ntt256_mgpu_forward", "ntt256_mgpu_inverse", "ntt256_mgpu_forward_batch",
     "ntt256_mgpu_synchronize", "ntt256_mgpu_destroy",
     "ntt256_vec_mul", "ntt256_to_montgomery", "ntt256_from_montgomery", "ntt256_coset_forward",
@@ -94,6 +95,9 @@ def lib() -> ctypes.CDLL:
         L.ntt256_ipc_close.argtypes = [ci, vp]
         L.ntt256_ipc_free.argtypes = [ci, vp]
         L.ntt256_peer_barrier.argtypes = [ci, ctypes.POINTER(vp), ci, ci, ctypes.c_ulonglong, vp]
+        L.ntt256_set_peer_barrier_timeout.argtypes = [ctypes.c_double]
+        L.ntt256_peer_sync_status.argtypes = [ci, vp, ctypes.POINTER(ctypes.c_ulonglong)]
+        L.ntt256_ctx_set_peer_sync.argtypes = [vp, ctypes.POINTER(vp), ci, ci, ctypes.c_double]
         L.ntt256_plan_describe.argtypes = [ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]
         L.ntt256_plan_describe.restype = ctypes.c_size_t
         L.ntt256_plan_describe_ex.argtypes = [ci, ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]

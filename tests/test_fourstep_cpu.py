@@ -162,3 +162,34 @@ def test_fourstep_two_gloo_ranks(built, tmp_path):
          "--master-port", "29611", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "FOURSTEP_GLOO_OK" in out.stdout
+
+
+def test_output_location_and_geometric_input_helpers():
+    """ntt_b200.dist.output_location / geometric_shard / geometric_output (used by bench.py's config-5 check
+    and by the 8-GPU 2^28 test) against the oracle at sizes where everything can be enumerated."""
+    import numpy as np
+
+    from ntt_b200 import dist as nd
+    from ntt_b200.api import FIELDS
+    from oracle import c_oracle as co
+
+    p, g = FIELDS["bn254_fr"]
+    c, h = 0x1234567890ABCDEF1122334455667788 % p, 7
+    for log_n, world in ((8, 4), (9, 2), (10, 8)):
+        n = 1 << log_n
+        xs = [c * pow(h, j, p) % p for j in range(n)]
+        x = np.array([[(v >> (32 * l)) & 0xFFFFFFFF for l in range(8)] for v in xs], dtype=np.uint32)
+        X = co.ntt(x, p, g)
+        Xi = co.array_to_ints(X)
+        for k in (0, 1, 5, n // 2, n - 1):
+            assert nd.geometric_output(c, h, p, g, log_n, k) == Xi[k]
+        shards = nd.scatter_input(x, log_n, world)
+        for r in range(world):
+            col, row = nd.geometric_shard(c, h, p, log_n, world, r)
+            ci, ri = co.array_to_ints(col), co.array_to_ints(row)
+            outer = np.array([[((a * b % p) >> (32 * l)) & 0xFFFFFFFF for l in range(8)] for a in ci for b in ri], dtype=np.uint32)
+            assert np.array_equal(outer, shards[r]), (log_n, world, r)
+        outs = nd.scatter_output_layout(X, log_n, world)
+        for k in range(n):
+            r, i = nd.output_location(k, log_n, world)
+            assert np.array_equal(outs[r][i], X[k])

@@ -21,7 +21,7 @@ torch.cuda.set_device(lr_)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
 p, g = FIELDS["bls12_381_fr"]
 ctx = Ntt256("bls12_381_fr", max_log_n=22, device=lr_)
-for fused, barrier in ((False, "nccl"), (True, "nccl"), (True, "flags")):
+for fused, barrier in ((False, "nccl"), (True, "nccl"), (True, "flags"), (True, "kernel")):
   for log_n in (14, 20):
     x = co.splitmix_elements(1 << log_n, p, 99 + log_n)          # same on every rank
     shard = nd.scatter_input(x, log_n, world)[rank]
@@ -49,6 +49,7 @@ for fused, barrier in ((False, "nccl"), (True, "nccl"), (True, "flags")):
     torch.cuda.synchronize()
     assert np.array_equal(out3.cpu().numpy().view(np.uint32).reshape(-1, 8), shard)
     dist.barrier()
+    fs.check()
     if fused:
         fs.close()
 # batch sharding: independent transforms, no collective
@@ -66,6 +67,136 @@ if rank == 0:
     print("MULTIGPU_OK", world)
 dist.destroy_process_group()
 '''
+
+
+_WORKER_24 = r'''
+import os, sys
+sys.path.insert(0, os.environ["NTT_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from ntt_b200 import dist as nd
+from ntt_b200.api import Ntt256, FIELDS
+from oracle import c_oracle as co
+rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr_)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
+# BASELINE config 4 at full size on every GPU of the box: all 2^24 outputs against the oracle
+# (/root/reference/src/big-num.cu:446-467 compares every element of every size it runs)
+log_n = 24
+for field in ("bn254_fr", "bls12_381_fr"):
+    p, g = FIELDS[field]
+    ctx = Ntt256(field, max_log_n=log_n, device=lr_)
+    shards = [co.splitmix_elements((1 << log_n) // world, p, 2400 + r) for r in range(world)] if rank == 0 else None
+    mine = co.splitmix_elements((1 << log_n) // world, p, 2400 + rank)
+    fs = nd.FourStep(ctx, log_n, world, rank, fused=True).load_shard(torch.from_numpy(mine.view(np.int32)).cuda().view(-1))
+    out = fs.forward().clone()
+    torch.cuda.synchronize()
+    fs.check()
+    gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+    dist.gather(out, gathered, dst=0)
+    if rank == 0:
+        X = nd.gather_output([t.cpu().numpy().view(np.uint32).reshape(-1, 8) for t in gathered], log_n, world)
+        x = nd.gather_input_layout(shards, log_n, world)
+        want = co.ntt(x, p, g, threads=max(1, min(co.max_threads(), os.cpu_count() or 1)))
+        assert np.array_equal(X, want), f"2^24 {field} over {world} GPUs differs from the oracle"
+    back = fs.inverse().clone()
+    torch.cuda.synchronize()
+    assert np.array_equal(back.cpu().numpy().view(np.uint32).reshape(-1, 8), mine)
+    dist.barrier()
+    fs.close()
+    ctx.close()
+if rank == 0:
+    print("MULTIGPU24_OK", world)
+dist.destroy_process_group()
+'''
+
+_WORKER_28 = r'''
+import os, sys
+sys.path.insert(0, os.environ["NTT_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from ntt_b200 import dist as nd
+from ntt_b200.api import Ntt256, FIELDS
+rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr_)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
+# BASELINE config 5: 2^28 points (8 GiB) over 8 GPUs.  x[j] = c*h^j, so X[k] = c(h^n - 1)/(h w^k - 1):
+# 512 sampled outputs per rank are checked against the closed form, then the distributed inverse must
+# return the input shard bit for bit.
+p, g = FIELDS["bn254_fr"]
+log_n = 28
+n = 1 << log_n
+c, h = 0x1234567890ABCDEF1122334455667788 % p, 7
+ctx = Ntt256("bn254_fr", max_log_n=log_n, device=lr_)
+fs = nd.FourStep(ctx, log_n, world, rank, fused=True)
+col, row = nd.geometric_shard(c, h, p, log_n, world, rank, fs.log_r)
+R, w = col.shape[0], row.shape[0]
+a = torch.from_numpy(col.view(np.int32)).cuda().view(R, 1, 8).expand(R, w, 8).contiguous().view(-1)
+b = torch.from_numpy(row.view(np.int32)).cuda().view(1, w, 8).expand(R, w, 8).contiguous().view(-1)
+ctx.vec_mul(a, b, out=a)
+del b
+src = a.clone()
+fs.load_shard(a)
+out = fs.forward()
+torch.cuda.synchronize()
+fs.check()
+rng = np.random.default_rng(28 + rank)
+ks = [0, 1, n - 1, n // 2, n // 2 + 7] + [int(v) for v in rng.integers(0, n, size=4096)]
+checked = 0
+for k in ks:
+    owner, idx = nd.output_location(k, log_n, world, fs.log_r)
+    if owner != rank:
+        continue
+    v = out.view(-1)[8 * idx: 8 * idx + 8].cpu().numpy().view(np.uint32)
+    assert sum(int(v[i]) << (32 * i) for i in range(8)) == nd.geometric_output(c, h, p, g, log_n, k), (rank, k)
+    checked += 1
+assert checked >= 256
+back = fs.inverse()
+torch.cuda.synchronize()
+assert torch.equal(back.view(-1), src.view(-1)), "inverse(forward(shard)) != shard at 2^28"
+t = torch.tensor([checked], device="cuda")
+dist.all_reduce(t)
+fs.check()
+dist.barrier()
+fs.close()
+if rank == 0:
+    print("MULTIGPU28_OK", world, int(t.item()))
+dist.destroy_process_group()
+'''
+
+
+def _run_workers(tmp_path, source, world, port, timeout=1500):
+    script = tmp_path / "worker.py"
+    script.write_text(source)
+    env = dict(os.environ, NTT_ROOT=ROOT)
+    return subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+         "127.0.0.1", "--master-port", str(port), str(script)], env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_config4_full_2p24_over_all_gpus(tmp_path):
+    """Every output of the 2^24-point transform on 2/4/8 GPUs against the oracle, both fields, the default
+    exchange (peer stores + synchronisation folded into the kernels), then the distributed inverse."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("needs CUDA")
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("single-GPU box")
+    out = _run_workers(tmp_path, _WORKER_24, 1 << (n.bit_length() - 1), 29641)
+    assert out.returncode == 0, (out.stdout[-1500:] + out.stderr[-3000:])
+    assert "MULTIGPU24_OK" in out.stdout
+
+
+def test_config5_2p28_over_8_gpus_closed_form(tmp_path):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("needs CUDA")
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs the 8 GPUs of one box")
+    out = _run_workers(tmp_path, _WORKER_28, 8, 29651)
+    assert out.returncode == 0, (out.stdout[-1500:] + out.stderr[-3000:])
+    assert "MULTIGPU28_OK" in out.stdout
 
 
 def test_fourstep_and_batch_over_nccl(tmp_path):
