@@ -83,6 +83,9 @@ int ntt256_ctx_set_small_transform_limit(ntt256_ctx* ctx, long long max_elements
  * for ntt256_forward/inverse[_batch]; 0 restores the automatic choice.  Tiles are limited to 2^11
  * elements below 3. */
 int ntt256_ctx_set_elements_per_thread(ntt256_ctx* ctx, int log2_elements);
+/* Four-elements-per-thread passes run on a kernel instance compiled for three resident CTAs per SM (<= 85
+ * registers, 24 warps per SM) when the CTA has <= 256 threads; 0 selects the 128-register instance. */
+int ntt256_ctx_set_dense_pass4(ntt256_ctx* ctx, int enable);
 /* Twiddle representation of the pass kernels.  1 (the default whenever p < 2^254, e.g. BN254 Fr): tables
  * hold 64-byte pairs (w, floor(w 2^256 / p)) and a twiddle product is a Shoup/Barrett multiplication
  * (99 wide + 16 low 32-bit multiplies, csrc/field_shoup.cuh); 0 (the only choice for 255-bit moduli such as
@@ -127,6 +130,18 @@ int ntt256_coset_forward(ntt256_ctx* ctx, void* d_data, int log_n, int batch, co
                          ntt256_stream stream);
 int ntt256_coset_inverse(ntt256_ctx* ctx, void* d_data, int log_n, int batch, const uint32_t shift[8],
                          ntt256_stream stream);
+/* Transform, then multiply output k by d_mul_mont[k] -- a caller-owned device vector of batch * 2^log_n
+ * elements in MONTGOMERY form (ntt256_to_montgomery), so that the result is the plain product
+ * NTT(x)[k] * b[k] (resp. iNTT(x)[k] * b[k]): the pointwise-product step that follows a transform in a
+ * polynomial multiplication, fused into the stores of the last pass (no extra trip through HBM). */
+int ntt256_forward_mul(ntt256_ctx* ctx, void* d_data, const void* d_mul_mont, int log_n, int batch, ntt256_stream stream);
+int ntt256_inverse_mul(ntt256_ctx* ctx, void* d_data, const void* d_mul_mont, int log_n, int batch, ntt256_stream stream);
+/* Where the companions run.  1: the coset shift multiplies elements inside the first pass (forward) / last pass
+ * (inverse) and the pointwise product inside the last pass; 0: separate element-wise kernels before / after the
+ * passes; -1 (default): fused for calls of at most 2^17 elements (saves a launch), separate above (one more
+ * product per element costs the same wherever it runs on this multiplier-bound path, and the element-wise
+ * kernel runs at full occupancy).  Same bits either way. */
+int ntt256_ctx_set_fused_companions(ntt256_ctx* ctx, int enable);
 
 /* Multi-GPU four-step pieces (SURVEY.md par. 8e).  One process per GPU; the all-to-all between
  * the two calls is done by the caller (torch.distributed / NCCL, see ntt_b200/dist.py).

@@ -173,6 +173,26 @@ class Ntt256:
         self._check(self._L.ntt256_coset_inverse(self._h, ptr, log_n, batch, _u32p(_limbs(shift)), _stream_handle(stream)))
         return data
 
+    def forward_mul(self, data, mul_mont, log_n: int, batch: int = 1, stream=None):
+        """data <- NTT(data) * mul (element-wise); `mul_mont` holds batch * 2^log_n elements in Montgomery form."""
+        n = batch << log_n
+        self._check(self._L.ntt256_forward_mul(self._h, _device_ptr(data, n), _device_ptr(mul_mont, n), log_n, batch,
+                                               _stream_handle(stream)))
+        return data
+
+    def inverse_mul(self, data, mul_mont, log_n: int, batch: int = 1, stream=None):
+        n = batch << log_n
+        self._check(self._L.ntt256_inverse_mul(self._h, _device_ptr(data, n), _device_ptr(mul_mont, n), log_n, batch,
+                                               _stream_handle(stream)))
+        return data
+
+    def set_dense_pass4(self, enable: bool):
+        self._check(self._L.ntt256_ctx_set_dense_pass4(self._h, int(bool(enable))))
+
+    def set_fused_companions(self, enable):
+        """True / False: companions inside the end passes / as separate kernels; None: by call size (default)."""
+        self._check(self._L.ntt256_ctx_set_fused_companions(self._h, -1 if enable is None else int(bool(enable))))
+
     def fourstep_step1(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
         ptr = _device_ptr(shard, 1 << (log_n - log_p))
         self._check(self._L.ntt256_fourstep_step1(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))

@@ -15,7 +15,8 @@
 
 #include "../../include/ntt256.h"
 #include "hostfield.h"
-#include "ntt_kernels.cuh"
+#include "aux_kernels.cuh"
+#include "pass_launch.h"
 #include "plan.h"
 
 using namespace ntt256;
@@ -60,10 +61,16 @@ struct ntt256_ctx {
   int coalesce_bits = 2;
   U256 ninv[64];                          // Montgomery form of 2^-k, filled on first use
   bool ninv_ok[64] = {};
+  bool dense_pass4 = true;                // four elements per thread: three CTAs of <= 256 threads per SM
   int force_group_bits = 0;               // 0: automatic; 1..3: elements per thread = 2^k for every plan
   long long small_limit = 1ll << 17;      // batch*n at or below this: four (half of it: two) elements per thread
   bool auto_tile = true;                  // shrink the tile for small problems so the grid fills the chip
   bool zero_copy_host = true;             // *_host entry points: first/last pass access pinned host memory directly
+  // coset shift / pointwise product inside the first / last pass: 1 always, 0 never, -1 (default) for calls of
+  // at most 2^17 elements.  The companions cost one more product per element wherever they run; on this
+  // multiplier-bound path the separate element-wise kernel (full occupancy, HBM at 80 %) is as fast as the
+  // fused form from ~2^18 elements on, and the fused form only saves a launch (profiles/r02_companions.jsonl).
+  int fuse_companions = -1;
   std::map<int, uint4*> loc_scaled;       // log_n -> (1/n) * loc[] : folds the inverse scaling into a round twiddle
   // streamed pass-twiddle arrays, keyed by (plan id, pass index, direction)
   std::map<std::tuple<unsigned long long, int, int>, uint4*> tw_streams;
@@ -74,7 +81,8 @@ struct ntt256_ctx {
     U256 shift;
     int log_n, lo_bits;
     uint4 *hi, *lo;
-    uint4* direct;  // s^j for every j < 2^log_n (32 B * 2^log_n), or null: see kCosetDirect* below
+    uint4* direct;  // s^j for every j < 2^log_n in the context's twiddle format (32 or 64 B each), or null
+    bool direct_shoup;
   };
   std::vector<CosetTables> cosets;        // small cache of shift^j tables (forward and inverse shifts)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;   // pipelined host batches
@@ -129,8 +137,15 @@ int build_power_table(ntt256_ctx* ctx, uint4** out, const U256& base_mont, int b
     b = ctx->hf.mul(b, b);
   }
   uint4* d_pw = nullptr;
-  CTX_CUDA(cudaMalloc((void**)&d_pw, pw.size() * 4));
-  CTX_CUDA(cudaMemcpy(d_pw, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));
+  auto fail = [&](const char* what) {
+    if (d_pw) cudaFree(d_pw);
+    cudaFree(*out);
+    *out = nullptr;
+    ctx->last_err = what;
+    return NTT256_ERR_CUDA;
+  };
+  if (cudaMalloc((void**)&d_pw, pw.size() * 4) != cudaSuccess) return fail("cudaMalloc (power seeds)");
+  if (cudaMemcpy(d_pw, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail("cudaMemcpy (power seeds)");
   Fe one, pinv;
   to_u32(ctx->hf.one, one.v);
   to_u32(ctx->hf.pinv, pinv.v);
@@ -138,9 +153,8 @@ int build_power_table(ntt256_ctx* ctx, uint4** out, const U256& base_mont, int b
   const unsigned blocks = (unsigned)((count + threads - 1) / threads);
   twiddle_powers_kernel<<<blocks, threads>>>(*out, d_pw, bits, 0ull, count, ctx->fp, one, shoup_entries ? 1 : 0, pinv);
   ++ctx->launches;
-  CTX_CUDA(cudaGetLastError());
-  CTX_CUDA(cudaDeviceSynchronize());
-  CTX_CUDA(cudaFree(d_pw));
+  if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return fail("twiddle_powers_kernel");
+  cudaFree(d_pw);
   return NTT256_OK;
 }
 
@@ -281,24 +295,22 @@ struct IoSpec {  // optional out-of-place ends of a plan (device-visible pointer
   const void* src_first = nullptr;
   void* dst_last = nullptr;
 };
+struct FuseSpec {  // element-wise companions fused into the first / last pass (PassArgs::in_scale ...)
+  const uint4* in_scale = nullptr;
+  const uint4* out_scale = nullptr;
+  const uint4* out_mul = nullptr;
+};
 
-// The pass kernel for 2^group_bits elements per thread.
-void launch_pass(bool shoup, int group_bits, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream,
+// The pass kernel for 2^group_bits elements per thread; FZ instances only for launches that carry companions.
+void launch_pass(bool shoup, int group_bits, bool dense, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream,
                  const uint4* in, uint4* out, const PassArgs& A) {
+  const bool fz = A.in_scale || A.out_scale || A.out_mul;
   if (shoup) {
-    if (group_bits == 3)
-      ntt_pass_kernel<true><<<grid, threads, smem, stream>>>(in, out, A);
-    else if (group_bits == 2)
-      ntt_pass4_kernel<true><<<grid, threads, smem, stream>>>(in, out, A);
-    else
-      ntt_pass2_kernel<true><<<grid, threads, smem, stream>>>(in, out, A);
+    if (fz) launch_pass_inst<true, true>(group_bits, dense, grid, threads, smem, stream, in, out, A);
+    else launch_pass_inst<true, false>(group_bits, dense, grid, threads, smem, stream, in, out, A);
   } else {
-    if (group_bits == 3)
-      ntt_pass_kernel<false><<<grid, threads, smem, stream>>>(in, out, A);
-    else if (group_bits == 2)
-      ntt_pass4_kernel<false><<<grid, threads, smem, stream>>>(in, out, A);
-    else
-      ntt_pass2_kernel<false><<<grid, threads, smem, stream>>>(in, out, A);
+    if (fz) launch_pass_inst<false, true>(group_bits, dense, grid, threads, smem, stream, in, out, A);
+    else launch_pass_inst<false, false>(group_bits, dense, grid, threads, smem, stream, in, out, A);
   }
 }
 
@@ -314,7 +326,7 @@ const U256& inv_pow2(ntt256_ctx* ctx, int k) {
 // sync: 0 none; 1 the first pass waits for every rank's epoch; 2 the last pass publishes this rank's epoch
 int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long batch_stride, int batch, bool inverse,
              int scale_log_n, cudaStream_t stream, const PeerSpec* peer = nullptr, const IoSpec* io = nullptr,
-             int sync = 0) {
+             int sync = 0, const FuseSpec* fuse = nullptr) {
   PassArgs A;
   std::memset(&A, 0, sizeof(A));
   A.f = ctx->fp;
@@ -395,7 +407,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
             to_u32(sh ? u256_small(1) : ctx->hf.one, G.one);
             const int Tg = G.pd.T;
             dim3 ggrid((unsigned)(1ull << G.pd.nblk_bits), 1, 1);
-            launch_pass(sh, plan.group_bits, ggrid, 1u << (Tg - plan.group_bits), (size_t)32 << Tg, stream,
+            launch_pass(sh, plan.group_bits, ctx->dense_pass4, ggrid, 1u << (Tg - plan.group_bits), (size_t)32 << Tg, stream,
                         (const uint4*)d_data, (uint4*)d_data, G);
             ++ctx->launches;
             CTX_CUDA(cudaGetLastError());
@@ -415,6 +427,9 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
       A.peer_shift = peer->shift;
       A.peer_rank = peer->rank;
     }
+    A.in_scale = (fuse && i == 0) ? fuse->in_scale : nullptr;
+    A.out_scale = (fuse && i + 1 == plan.passes.size()) ? fuse->out_scale : nullptr;
+    A.out_mul = (fuse && i + 1 == plan.passes.size()) ? fuse->out_mul : nullptr;
     A.sync_mode = 0;
     if (sync && ctx->sync_nranks > 1) {
       if ((sync & 1) && i == 0) A.sync_mode |= 1;
@@ -438,7 +453,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
     // first pass may read from `src_first`, last pass may write to `dst_last` (host-mapped buffers)
     const uint4* pin = (i == 0 && io && io->src_first) ? (const uint4*)io->src_first : (const uint4*)d_data;
     uint4* pout = (i + 1 == plan.passes.size() && io && io->dst_last) ? (uint4*)io->dst_last : (uint4*)d_data;
-    launch_pass(sh, GB, grid, threads, smem, stream, pin, pout, A);
+    launch_pass(sh, GB, ctx->dense_pass4, grid, threads, smem, stream, pin, pout, A);
     ++ctx->launches;
     CTX_CUDA(cudaGetLastError());
   }
@@ -465,7 +480,7 @@ int run_tiny(ntt256_ctx* ctx, void* d_data, int log_n, unsigned long long batch,
 }
 
 int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse, cudaStream_t stream,
-              const IoSpec* io = nullptr) {
+              const IoSpec* io = nullptr, const FuseSpec* fuse = nullptr) {
   if (!ctx || !d_data || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
   CTX_CUDA(cudaSetDevice(ctx->device));
   if (log_n < 3) return run_tiny(ctx, d_data, log_n, (unsigned long long)batch, inverse, stream);
@@ -487,6 +502,11 @@ int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse,
       key.group_bits = 2;
       key.tile_bits = std::min(9, log_n);
       key.coalesce = 0;
+    } else if (E > (1ll << 19) && E <= (1ll << 20) && log_n >= 10 && ctx->dense_pass4) {
+      // calls of about 2^20 elements: four elements per thread in 2^10-element tiles on the three-CTAs-per-SM instance
+      // (24 warps per SM): 2-5 % ahead of eight per thread here, level with it below (profiles/r02_shapes_mid.jsonl)
+      key.group_bits = 2;
+      key.tile_bits = 10;
     } else if (E <= (1ll << 20)) {
       key.tile_bits = std::min(std::min(10, ctx->tile_bits), log_n);
     } else if (log_n < ctx->tile_bits) {
@@ -509,8 +529,13 @@ int transform(ntt256_ctx* ctx, void* d_data, int log_n, int batch, bool inverse,
       io_slice.src_first = io->src_first ? (const char*)io->src_first + off : nullptr;
       io_slice.dst_last = io->dst_last ? (char*)io->dst_last + off : nullptr;
     }
+    FuseSpec fuse_slice;
+    if (fuse) {
+      fuse_slice = *fuse;
+      if (fuse->out_mul) fuse_slice.out_mul = fuse->out_mul + 2 * ((size_t)b0 << log_n);  // per call, not per transform
+    }
     rc = run_plan(ctx, *plan, p, 1ull << log_n, nb, inverse, inverse ? log_n : -1, stream, nullptr,
-                  io ? &io_slice : nullptr);
+                  io ? &io_slice : nullptr, 0, fuse ? &fuse_slice : nullptr);
     if (rc) return rc;
   }
   return NTT256_OK;
@@ -606,8 +631,8 @@ int transform_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, in
 // Multiplied-out shift^j tables trade 32 B/element of memory and HBM traffic for one of the two
 // products of the scaling pass (2^24: 0.53 -> 0.3 ms).  One table may take 1 GiB (n <= 2^25), all
 // cached ones together 2 GiB; larger transforms keep the two small factored tables.
-constexpr size_t kCosetDirectMax = (size_t)1 << 30;
-constexpr size_t kCosetDirectBudget = (size_t)2 << 30;
+constexpr size_t kCosetDirectMax = (size_t)2 << 30;     // 2^25 points in Montgomery format, 2^24 as Shoup pairs
+constexpr size_t kCosetDirectBudget = (size_t)4 << 30;
 
 void drop_oldest_coset(ntt256_ctx* ctx) {
   auto& c = ctx->cosets.front();
@@ -633,23 +658,35 @@ int get_coset_tables(ntt256_ctx* ctx, const U256& shift_plain, int log_n, const 
   int rc = build_power_table(ctx, &t.lo, sm, t.lo_bits);
   if (rc) return rc;
   rc = build_power_table(ctx, &t.hi, pow2k(ctx->hf, sm, t.lo_bits), log_n - t.lo_bits);
-  if (rc) return rc;
+  if (rc) {
+    cudaFree(t.lo);
+    return rc;
+  }
   t.direct = nullptr;
-  const size_t dbytes = (size_t)32 << log_n;
+  t.direct_shoup = ctx->shoup;
+  const size_t dbytes = (size_t)(ctx->shoup ? 64 : 32) << log_n;
   if (dbytes <= kCosetDirectMax) {
     auto cached = [&] {
       size_t sum = 0;
       for (auto& c : ctx->cosets)
-        if (c.direct) sum += (size_t)32 << c.log_n;
+        if (c.direct) sum += (size_t)(c.direct_shoup ? 64 : 32) << c.log_n;
       return sum;
     };
     while (!ctx->cosets.empty() && cached() + dbytes > kCosetDirectBudget) drop_oldest_coset(ctx);
     if (cudaMalloc((void**)&t.direct, dbytes) == cudaSuccess) {
       const unsigned long long count = 1ull << log_n;
-      coset_table_kernel<<<(unsigned)((count + 127) / 128), 128>>>(t.direct, count, t.lo_bits, t.hi, t.lo, ctx->fp);
+      Fe pinv;
+      to_u32(ctx->hf.pinv, pinv.v);
+      coset_table_kernel<<<(unsigned)((count + 127) / 128), 128>>>(t.direct, count, t.lo_bits, t.hi, t.lo, ctx->fp,
+                                                                   ctx->shoup ? 1 : 0, pinv);
       ++ctx->launches;
-      CTX_CUDA(cudaGetLastError());
-      CTX_CUDA(cudaDeviceSynchronize());  // one-off: later calls may use any stream
+      if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {  // one-off sync
+        cudaFree(t.direct);
+        cudaFree(t.hi);
+        cudaFree(t.lo);
+        ctx->last_err = "coset_table_kernel failed";
+        return NTT256_ERR_CUDA;
+      }
     } else {
       cudaGetLastError();  // no memory to spare: keep the factored tables
       t.direct = nullptr;
@@ -667,8 +704,8 @@ int coset_scale(ntt256_ctx* ctx, void* d_data, int log_n, int batch, const U256&
   const unsigned long long n = (unsigned long long)batch << log_n;
   const int threads = 128;
   if (t->direct)
-    coset_scale_direct_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>((uint4*)d_data, n, log_n,
-                                                                                             t->direct, ctx->fp);
+    coset_scale_direct_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(
+        (uint4*)d_data, n, log_n, t->direct, ctx->fp, t->direct_shoup ? 1 : 0);
   else
     coset_scale_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>((uint4*)d_data, n, log_n,
                                                                                       t->lo_bits, t->hi, t->lo, ctx->fp);
@@ -680,6 +717,16 @@ int coset_scale(ntt256_ctx* ctx, void* d_data, int log_n, int batch, const U256&
 }  // namespace
 
 extern "C" {
+
+// 2^229 < p and 5p + 2^226 < 2^256: what the Shoup / wide-lazy kernels need (BN254 Fr: 2^256 / p = 5.29).  The
+// lower bound keeps the slack of the approximate corrections (up to 2^224) below p, so that a - b + 3p > 0.
+static bool shoup_capable(const U256& P) {
+  if (u256_bitlen(P) > 254 || u256_bitlen(P) < 230) return false;
+  U256 p2, p4, p5, t;
+  u256_add(p2, P, P);
+  if (u256_add(p4, p2, p2) || u256_add(p5, p4, P)) return false;
+  return u256_add(t, p5, U256{{0, 0, 0, 1ull << 34}}) == 0;
+}
 
 int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const uint32_t g[8], int max_log_n) {
   if (!out || !p || !g || max_log_n < 1 || max_log_n > 32) return NTT256_ERR_ARG;
@@ -705,10 +752,19 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
     U256 pbar;
     u256_sub(pbar, u256_small(0), P);  // 2^256 - p
     u256_to_limbs(pbar, ctx->fp.pbar);
+    U256 p2bar;
+    u256_sub(p2bar, u256_small(0), P2);  // 2^256 - 2p
+    u256_to_limbs(p2bar, ctx->fp.p2bar);
   }
   ctx->fp.np0 = (u32)ctx->hf.np0;
-  // shoup_mul's remainder lies in [0, 3p): it must fit 256 bits (field_shoup.cuh)
-  ctx->shoup = u256_bitlen(P) <= 254;
+  // Shoup twiddles come with the wide-lazy add/sub policy (field_wl.cuh): sums reach 4p + 2^225 and differences
+  // a - b + 3p reach 5p + 2^224, which must fit 256 bits; shoup_mul's own remainder stays below 3p
+  ctx->shoup = shoup_capable(P);
+  if (ctx->shoup) {
+    U256 p3;
+    u256_add(p3, P2, P);
+    u256_to_limbs(p3, ctx->fp.kp);
+  }
   ctx->g_mont = ctx->hf.to_mont(G);
   ctx->wN = root_of_unity(ctx->hf, ctx->g_mont, max_log_n);
   ctx->wN_inv = ctx->hf.inv(ctx->wN);
@@ -766,14 +822,9 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) ctx->tw_stream_limit = total_b / 16;
   }
-  if (cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMaxTileBits) !=
-          cudaSuccess ||
-      cudaFuncSetAttribute(ntt_pass4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess ||
-      cudaFuncSetAttribute(ntt_pass2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess ||
-      cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMaxTileBits) !=
-          cudaSuccess ||
-      cudaFuncSetAttribute(ntt_pass4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess ||
-      cudaFuncSetAttribute(ntt_pass2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 11) != cudaSuccess)
+  const int big = 32 << kMaxTileBits, small = 32 << 11;
+  if (!pass_inst_set_smem<false, false>(big, small) || !pass_inst_set_smem<false, true>(big, small) ||
+      !pass_inst_set_smem<true, false>(big, small) || !pass_inst_set_smem<true, true>(big, small))
     return fail(NTT256_ERR_CUDA);
   rc = build_twiddle_tables(ctx);
   if (rc) return fail(rc);
@@ -889,13 +940,28 @@ int ntt256_from_montgomery(ntt256_ctx* ctx, void* d_data, unsigned long long n, 
   return vec_scale(ctx, d_data, n, u256_small(1), (cudaStream_t)stream);  // montmul(1, x) = x/R
 }
 
+static bool fuse_here(const ntt256_ctx* ctx, int log_n, int batch) {
+  if (log_n < 3) return false;
+  if (ctx->fuse_companions >= 0) return ctx->fuse_companions != 0;
+  return ((long long)batch << log_n) <= (1ll << 17);
+}
 int ntt256_coset_forward(ntt256_ctx* ctx, void* d_data, int log_n, int batch, const uint32_t shift[8],
                          ntt256_stream stream) {
   if (!ctx || !d_data || !shift || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
   U256 s = u256_from_limbs(shift);
   if (u256_is_zero(s) || u256_cmp(s, ctx->hf.p) >= 0) return NTT256_ERR_ARG;
   CTX_CUDA(cudaSetDevice(ctx->device));
-  int rc = coset_scale(ctx, d_data, log_n, batch, s, (cudaStream_t)stream);
+  // shift^j multiplies the elements as the first pass loads them (one more product on values already in
+  // registers, no extra trip through HBM) whenever the multiplied-out table exists
+  const ntt256_ctx::CosetTables* t = nullptr;
+  int rc = get_coset_tables(ctx, s, log_n, &t);
+  if (rc) return rc;
+  if (t->direct && fuse_here(ctx, log_n, batch)) {
+    FuseSpec fz;
+    fz.in_scale = t->direct;
+    return transform(ctx, d_data, log_n, batch, false, (cudaStream_t)stream, nullptr, &fz);
+  }
+  rc = coset_scale(ctx, d_data, log_n, batch, s, (cudaStream_t)stream);
   if (rc) return rc;
   return transform(ctx, d_data, log_n, batch, false, (cudaStream_t)stream);
 }
@@ -906,10 +972,44 @@ int ntt256_coset_inverse(ntt256_ctx* ctx, void* d_data, int log_n, int batch, co
   U256 s = u256_from_limbs(shift);
   if (u256_is_zero(s) || u256_cmp(s, ctx->hf.p) >= 0) return NTT256_ERR_ARG;
   CTX_CUDA(cudaSetDevice(ctx->device));
-  int rc = transform(ctx, d_data, log_n, batch, true, (cudaStream_t)stream);
-  if (rc) return rc;
   U256 sinv = ctx->hf.from_mont(ctx->hf.inv(ctx->hf.to_mont(s)));
+  const ntt256_ctx::CosetTables* t = nullptr;
+  int rc = get_coset_tables(ctx, sinv, log_n, &t);
+  if (rc) return rc;
+  if (t->direct && fuse_here(ctx, log_n, batch)) {
+    FuseSpec fz;
+    fz.out_scale = t->direct;  // shift^-k multiplies the outputs of the last pass before they are stored
+    return transform(ctx, d_data, log_n, batch, true, (cudaStream_t)stream, nullptr, &fz);
+  }
+  rc = transform(ctx, d_data, log_n, batch, true, (cudaStream_t)stream);
+  if (rc) return rc;
   return coset_scale(ctx, d_data, log_n, batch, sinv, (cudaStream_t)stream);
+}
+
+static int transform_mul(ntt256_ctx* ctx, void* d_data, const void* d_mul_mont, int log_n, int batch, bool inverse,
+                         cudaStream_t stream) {
+  if (!ctx || !d_data || !d_mul_mont || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  if (fuse_here(ctx, log_n, batch)) {
+    FuseSpec fz;
+    fz.out_mul = (const uint4*)d_mul_mont;
+    return transform(ctx, d_data, log_n, batch, inverse, stream, nullptr, &fz);
+  }
+  int rc = transform(ctx, d_data, log_n, batch, inverse, stream);
+  if (rc) return rc;
+  return ntt256_vec_mul(ctx, d_data, d_data, d_mul_mont, (unsigned long long)batch << log_n, 1, (ntt256_stream)stream);
+}
+int ntt256_forward_mul(ntt256_ctx* ctx, void* d_data, const void* d_mul_mont, int log_n, int batch, ntt256_stream stream) {
+  return transform_mul(ctx, d_data, d_mul_mont, log_n, batch, false, (cudaStream_t)stream);
+}
+int ntt256_inverse_mul(ntt256_ctx* ctx, void* d_data, const void* d_mul_mont, int log_n, int batch, ntt256_stream stream) {
+  return transform_mul(ctx, d_data, d_mul_mont, log_n, batch, true, (cudaStream_t)stream);
+}
+int ntt256_ctx_set_fused_companions(ntt256_ctx* ctx, int enable) {
+  if (!ctx) return NTT256_ERR_ARG;
+  if (enable < -1 || enable > 1) return NTT256_ERR_ARG;
+  ctx->fuse_companions = enable;
+  return NTT256_OK;
 }
 
 static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log_r, int log_p, int rank,
@@ -1174,11 +1274,12 @@ int ntt256_ctx_set_peer_sync(ntt256_ctx* ctx, void* const* flag_bufs, int nranks
 
 int ntt256_ctx_set_twiddle_mode(ntt256_ctx* ctx, int shoup) {
   if (!ctx || (shoup != 0 && shoup != 1)) return NTT256_ERR_ARG;
-  if (shoup && u256_bitlen(ctx->hf.p) > 254) return NTT256_ERR_FIELD;
+  if (shoup && !shoup_capable(ctx->hf.p)) return NTT256_ERR_FIELD;
   if ((shoup != 0) == ctx->shoup) return NTT256_OK;
   CTX_CUDA(cudaSetDevice(ctx->device));
   CTX_CUDA(cudaDeviceSynchronize());
   free_twiddle_tables(ctx);
+  while (!ctx->cosets.empty()) drop_oldest_coset(ctx);
   ctx->shoup = shoup != 0;
   return build_twiddle_tables(ctx);
 }
@@ -1188,6 +1289,12 @@ int ntt256_ctx_get_twiddle_mode(const ntt256_ctx* ctx) { return ctx && ctx->shou
 int ntt256_ctx_set_elements_per_thread(ntt256_ctx* ctx, int log2_elements) {
   if (!ctx || log2_elements < 0 || log2_elements > 3) return NTT256_ERR_ARG;
   ctx->force_group_bits = log2_elements;
+  return NTT256_OK;
+}
+
+int ntt256_ctx_set_dense_pass4(ntt256_ctx* ctx, int enable) {
+  if (!ctx) return NTT256_ERR_ARG;
+  ctx->dense_pass4 = enable != 0;
   return NTT256_OK;
 }
 

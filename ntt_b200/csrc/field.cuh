@@ -32,6 +32,8 @@ struct FieldParams {
   u32 p[8];     // modulus
   u32 p2[8];    // 2p (fits: p < 2^255)
   u32 pbar[8];  // 2^256 - p (shoup_mul, field_shoup.cuh)
+  u32 p2bar[8]; // 2^256 - 2p (field_wl.cuh)
+  u32 kp[8];    // 3p: added to a difference so that it cannot go negative (field_wl.cuh)
   u32 np0;      // -p^{-1} mod 2^32
   u32 pad[3];
 };

@@ -17,6 +17,7 @@
 
 #include "field.cuh"
 #include "field_shoup.cuh"
+#include "field_wl.cuh"
 #include "kernel_common.cuh"
 #include "plan.h"
 
@@ -60,6 +61,15 @@ struct PassArgs {
   u32 scaleq[8];
   u32 r2[8];    // R^2 mod p: plain -> Montgomery form (only to derive companions when a table is generated)
   u32 pinv[8];  // p^-1 mod 2^256
+  // Companions fused into the end passes (SURVEY.md par. 8f row 2; the reference's bellperson-style kernel
+  // premultiplies inside the pass as well, /root/reference/src/GZKP-NTT.cu:423-429).  Tables in the
+  // context's twiddle format, indexed by the element's natural index inside one transform:
+  //   in_scale : first pass, every loaded element is multiplied by in_scale[j]   (coset shift s^j)
+  //   out_scale: last pass, every output by out_scale[k] before it is made canonical (s^-k of a coset inverse)
+  //   out_mul  : last pass, every output by a caller-supplied Montgomery-form vector (pointwise product)
+  const uint4* in_scale;
+  const uint4* out_scale;
+  const uint4* out_mul;
   // Rank synchronisation folded into the passes (multi-GPU four-step, one process per GPU).  sync_mode bit 1
   // (arrive, last pass of step 1): when the grid's last CTA has finished its peer stores it publishes
   // sync_epoch in every rank's flag buffer.  Bit 0 (wait, first pass of step 2): every CTA first waits
@@ -104,6 +114,15 @@ NTT_DEV void ld_table(u32* v, const uint4* tab, u32 idx) {
 NTT_DEV void mul_by(u32* x, const u32* w, const FieldParams& f) {
   u32 r[8];
   mont_mul(r, w, x, f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = r[k];
+}
+
+// x <- x * b / R for a lazy b (any value below 2^256) and a canonical x: the product of two variable
+// operands, e.g. transform outputs times a caller's Montgomery-form vector (= the plain product).
+NTT_DEV void mul_by_left(u32* x, const u32* b, const FieldParams& f) {
+  u32 r[8];
+  mont_mul(r, x, b, f);
 #pragma unroll
   for (int k = 0; k < 8; ++k) x[k] = r[k];
 }
@@ -178,21 +197,46 @@ NTT_DEV void bfly(u32* a, u32* b, const FieldParams& f) {
   }
 }
 
+// The same under the wide-lazy policy of Shoup contexts (field_wl.cuh).  to_mul: the difference is multiplied
+// by a twiddle next (any 256-bit value is a valid operand of shoup_mul), so it only needs to be non-negative.
+NTT_DEV void bfly_wl(u32* a, u32* b, const FieldParams& f, bool to_mul) {
+  u32 s[8], d[8];
+  add_wl(s, a, b, f);
+  if (to_mul) sub_wl_mul(d, a, b, f); else sub_wl(d, a, b, f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    a[k] = s[k];
+    b[k] = d[k];
+  }
+}
+
+// [0, 2p) -> [0, p) (Montgomery contexts) / anything the wide-lazy policy produces -> [0, p) (Shoup contexts)
+template <bool SH>
+NTT_DEV void canon(u32* x, const FieldParams& f) {
+  if constexpr (SH) canonicalize_wl(x, f); else canonicalize(x, f);
+}
+
 // NB DIF stages on the top NB bits of the GB-bit register index, with the constant twiddles of
 // the 2^NB-point sub-transform (powers of w_8), followed -- unless this is the last round of the
 // pass -- by the round twiddle w_{2^m}^(tau_lo * v) from the table.
 template <int GB, int NB, bool SH>
 NTT_DEV void round_compute(u32 (*x)[8], const PassArgs& A, const FieldParams& f, bool last, bool scaled, u32 lam0,
-                           int sb, int lowp) {
+                           int sb, int lowp, bool tail_mul) {
 #pragma unroll
   for (int k = 0; k < NB; ++k) {
     const int bit = GB - 1 - k;
 #pragma unroll
     for (int u = 0; u < (1 << GB); ++u) {
       if (u & (1 << bit)) continue;
-      bfly(x[u], x[u | (1 << bit)], f);
       const int t = (u >> (GB - NB)) & ((1 << (NB - 1 - k)) - 1);  // lower processed bits of u
       const int e8 = t << (3 - (NB - k));                           // twiddle as a power of w_8
+      if constexpr (SH) {
+        // the differences of the round's last stage meet the round / pass twiddle next (tail_mul), those with
+        // a constant twiddle meet it right here; only the others must come back into the lazy range themselves
+        bfly_wl(x[u], x[u | (1 << bit)], f, e8 != 0 || (k == NB - 1 && tail_mul));
+      } else {
+        bfly(x[u], x[u | (1 << bit)], f);
+      }
       if (e8) mul_tw<SH>(x[u | (1 << bit)], A.c8[e8 - 1], A.c8q[e8 - 1], f);
     }
   }
@@ -227,7 +271,9 @@ NTT_DEV void round_compute(u32 (*x)[8], const PassArgs& A, const FieldParams& f,
 // One pass.  GB = log2(elements per thread): 3 is the throughput configuration (radix-8 rounds,
 // 64 data registers); 2 halves the serial work per thread and doubles the number of warps, which
 // is what small, latency-bound transforms need.
-template <int GB, bool SH>
+// FZ: the launch carries element-wise companions (in_scale / out_scale / out_mul); plain transforms run the
+// FZ = false instances, whose code does not know about them.
+template <int GB, bool SH, bool FZ>
 NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs& A, u32* smem) {
   constexpr int NE = 1 << GB;
   const PassDesc& pd = A.pd;
@@ -291,6 +337,11 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
 #pragma unroll
         for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
         ld_global_256(x[u], gbase_in + 2 * (size_t)off);
+        if (FZ && A.in_scale != nullptr) {
+          u32 w[8], wq[8];
+          ld_tw<SH>(w, wq, A.in_scale, (u32)base_t + off);
+          mul_tw<SH>(x[u], w, wq, f);
+        }
       }
     } else {
       const u32 w0 = swz(lam0);
@@ -305,12 +356,15 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
     // ---- butterflies on the top nb bits of the group (+ round twiddle unless last)
     if (!gen) {
       const bool scaled = (r == A.scaled_round);
+      // every element with a processed bit set is multiplied after the round: by the round twiddle, or by the
+      // pass twiddle / the 1/n of an inverse when this is the last round
+      const bool tail_mul = !last || pd.has_tw || pd.scale_out;
       if (nb == 3) {
-        if constexpr (GB >= 3) round_compute<GB, 3, SH>(x, A, f, last, scaled, lam0, sb, lowp);
+        if constexpr (GB >= 3) round_compute<GB, 3, SH>(x, A, f, last, scaled, lam0, sb, lowp, tail_mul);
       } else if (nb == 2) {
-        if constexpr (GB >= 2) round_compute<GB, 2, SH>(x, A, f, last, scaled, lam0, sb, lowp);
+        if constexpr (GB >= 2) round_compute<GB, 2, SH>(x, A, f, last, scaled, lam0, sb, lowp, tail_mul);
       } else if (nb == 1) {
-        round_compute<GB, 1, SH>(x, A, f, last, scaled, lam0, sb, lowp);
+        round_compute<GB, 1, SH>(x, A, f, last, scaled, lam0, sb, lowp, tail_mul);
       }
     }
 
@@ -372,9 +426,28 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
 #pragma unroll
         for (int u = 0; u < NE; ++u) mul_tw<SH>(x[u], A.scale, A.scaleq, f);
       }
+      if (FZ && (A.out_scale != nullptr || A.out_mul != nullptr)) {
+#pragma unroll
+        for (int u = 0; u < NE; ++u) {
+          u32 off = (u32)base_t + g0;
+#pragma unroll
+          for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
+          u32 w[8], wq[8];
+          if (A.out_scale != nullptr) {
+            ld_tw<SH>(w, wq, A.out_scale, off);
+            mul_tw<SH>(x[u], w, wq, f);
+          }
+          if (A.out_mul != nullptr) {
+            // the vector is per call, not per transform: batches index it with the full offset
+            ld_table(w, A.out_mul, (u32)(base - base_t) + off);
+            canon<SH>(x[u], f);  // mont_mul wants its left operand below p
+            mul_by_left(x[u], w, f);
+          }
+        }
+      }
       if (pd.is_final) {
 #pragma unroll
-        for (int u = 0; u < NE; ++u) canonicalize(x[u], f);
+        for (int u = 0; u < NE; ++u) canon<SH>(x[u], f);
       }
       // a single-round pass loads and stores global memory in the same round: every thread of
       // the CTA must have loaded before any permuted store lands on another thread's input
@@ -434,198 +507,39 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const PassArgs
 // data_in == data_out: in place (the normal case).  They differ when the first / last pass of
 // a host-buffer transform reads / writes pinned host memory directly (zero-copy over PCIe, so the
 // transfer overlaps the pass instead of preceding / following it).
-template <bool SH>
+template <bool SH, bool FZ = false>
 __global__ void __launch_bounds__(512, 1)
 ntt_pass_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
   extern __shared__ u32 smem[];
-  ntt_pass_body<3, SH>(data_in, data_out, A, smem);
+  ntt_pass_body<3, SH, FZ>(data_in, data_out, A, smem);
 }
 
 // Four elements per thread (radix-4 rounds): twice the warps, half the serial work per thread --
 // used for small transforms, which are latency-bound with eight elements per thread.
-template <bool SH>
+template <bool SH, bool FZ = false>
 __global__ void __launch_bounds__(512, 1)
 ntt_pass4_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
   extern __shared__ u32 smem[];
-  ntt_pass_body<2, SH>(data_in, data_out, A, smem);
+  ntt_pass_body<2, SH, FZ>(data_in, data_out, A, smem);
+}
+
+// The same body compiled for three resident CTAs of 256 threads (<= 85 registers; 80 used, 24 bytes spilled):
+// 24 warps per SM instead of 16.  The path is bound by the latency of dependent wide multiplies, not by
+// memory, so the extra warps pay for the extra round of shared-memory exchange (tiles of <= 2^10 elements).
+template <bool SH, bool FZ = false>
+__global__ void __launch_bounds__(256, 3)
+ntt_pass4h_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
+  extern __shared__ u32 smem[];
+  ntt_pass_body<2, SH, FZ>(data_in, data_out, A, smem);
 }
 
 // Two elements per thread (radix-2 rounds): the lowest-latency shape, for transforms so small that
 // even the four-element kernel leaves most of the chip idle.
-template <bool SH>
+template <bool SH, bool FZ = false>
 __global__ void __launch_bounds__(1024, 1)
 ntt_pass2_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgs A) {
   extern __shared__ u32 smem[];
-  ntt_pass_body<1, SH>(data_in, data_out, A, smem);
-}
-
-// Transforms of 2 or 4 points: one thread per transform, exact radix-2 DIF + bit reversal.
-struct TinyArgs {
-  FieldParams f;
-  int log_n;
-  u32 w4[8];      // w_4 (or its inverse), Montgomery form
-  u32 scale[8];   // 1/n Montgomery form
-  int do_scale;
-  unsigned long long batch;
-};
-
-__global__ void ntt_tiny_kernel(uint4* __restrict__ data, const __grid_constant__ TinyArgs A) {
-  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= A.batch) return;
-  const FieldParams& f = A.f;
-  const int n = 1 << A.log_n;
-  uint4* p = data + 2 * t * n;
-  u32 x[4][8];
-  for (int i = 0; i < n; ++i) ld_global_256(x[i], p + 2 * i);
-  if (A.log_n == 1) {
-    bfly(x[0], x[1], f);
-  } else if (A.log_n == 2) {
-    bfly(x[0], x[2], f);
-    bfly(x[1], x[3], f);
-    mul_by(x[3], A.w4, f);
-    bfly(x[0], x[1], f);
-    bfly(x[2], x[3], f);
-    // bit reversal of a 4-point DIF: swap positions 1 and 2
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      u32 tmp = x[1][k];
-      x[1][k] = x[2][k];
-      x[2][k] = tmp;
-    }
-  }
-  for (int i = 0; i < n; ++i) {
-    if (A.do_scale) mul_by(x[i], A.scale, f);
-    canonicalize(x[i], f);
-    st_global_256(p + 2 * i, x[i]);
-  }
-}
-
-// out[i] = prod over set bits k of i of pw[k]   (pw[k] = w^(2^k) in Montgomery form), i.e. w^i.
-// `first` offsets the exponent: out[i] = w^(first + i).
-// shoup != 0: 64-byte entries (w plain, wq) instead of the 32-byte Montgomery form.
-__global__ void twiddle_powers_kernel(uint4* __restrict__ out, const uint4* __restrict__ pw, int nbits,
-                                      unsigned long long first, unsigned long long count,
-                                      const __grid_constant__ FieldParams f, const __grid_constant__ Fe one,
-                                      int shoup, const __grid_constant__ Fe pinv) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const unsigned long long e = first + i;
-  u32 acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = one.v[k];
-  for (int b = 0; b < nbits; ++b) {
-    if ((e >> b) & 1ull) {
-      u32 w[8];
-      ld_table(w, pw, (u32)b);
-      mul_by(acc, w, f);
-    }
-  }
-  canonicalize(acc, f);
-  if (!shoup) {
-    st_global_256(out + 2 * i, acc);
-    return;
-  }
-  u32 w[8], wq[8], unit[8] = {1, 0, 0, 0, 0, 0, 0, 0};
-  mont_mul(w, acc, unit, f);  // (w R) * 1 / R = w; acc is canonical, a valid left operand
-  canonicalize(w, f);
-  shoup_companion(wq, acc, pinv.v);
-  st_global_256(out + 4 * i, w);
-  st_global_256(out + 4 * i + 2, wq);
-}
-
-// ---------------------------------------------------------------- element-wise companions
-// (SURVEY.md par. 8f: the prover steps either side of an NTT -- pointwise product, Montgomery
-// form conversion, coset shift).  One thread per element, 256-bit loads/stores.
-//   mode 0: out = a*b      canonical in/out          (two products: (a*b/R) * R^2/R)
-//   mode 1: out = a*b/R    Montgomery-form in/out    (one product)
-__global__ void vec_mul_kernel(uint4* __restrict__ out, const uint4* __restrict__ a, const uint4* __restrict__ b,
-                               unsigned long long n, int mode, const __grid_constant__ FieldParams f,
-                               const __grid_constant__ Fe r2) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  u32 x[8], y[8];
-  ld_global_256(x, a + 2 * i);
-  ld_global_256(y, b + 2 * i);
-  mul_by(y, x, f);  // x canonical (< p) is a valid left operand
-  if (mode == 0) mul_by(y, r2.v, f);
-  canonicalize(y, f);
-  st_global_256(out + 2 * i, y);
-}
-
-// x <- c * x for a Montgomery-form constant c (R^2: to Montgomery form; 1: from Montgomery form)
-__global__ void vec_scale_kernel(uint4* __restrict__ data, unsigned long long n, const __grid_constant__ FieldParams f,
-                                 const __grid_constant__ Fe c) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  u32 x[8];
-  ld_global_256(x, data + 2 * i);
-  mul_by(x, c.v, f);
-  canonicalize(x, f);
-  st_global_256(data + 2 * i, x);
-}
-
-// x[j] <- s^j * x[j] with s^j = hi[j >> lo_bits] * lo[j & mask] (both tables in Montgomery form);
-// j is the index inside one transform of 2^log_n points (batched arrays repeat the pattern).
-__global__ void coset_scale_kernel(uint4* __restrict__ data, unsigned long long n, int log_n, int lo_bits,
-                                   const uint4* __restrict__ hi, const uint4* __restrict__ lo,
-                                   const __grid_constant__ FieldParams f) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const u32 j = (u32)(i & ((1ull << log_n) - 1ull));
-  u32 x[8], w[8];
-  ld_global_256(x, data + 2 * i);
-  ld_table(w, hi, j >> lo_bits);
-  mul_by(x, w, f);
-  ld_table(w, lo, j & ((1u << lo_bits) - 1u));
-  mul_by(x, w, f);
-  canonicalize(x, f);
-  st_global_256(data + 2 * i, x);
-}
-
-// table[j] <- s^j in Montgomery form, j < count: the two factored tables multiplied out once, so that
-// the scaling pass of a coset transform is one product per element instead of two.
-__global__ void coset_table_kernel(uint4* __restrict__ table, unsigned long long count, int lo_bits,
-                                   const uint4* __restrict__ hi, const uint4* __restrict__ lo,
-                                   const __grid_constant__ FieldParams f) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  u32 a[8], b[8];
-  ld_table(a, hi, (u32)(i >> lo_bits));
-  ld_table(b, lo, (u32)i & ((1u << lo_bits) - 1u));
-  mul_by(a, b, f);  // (s^hi R)(s^lo R)/R = s^j R
-  canonicalize(a, f);
-  st_global_256(table + 2 * i, a);
-}
-
-// x[j] <- s^j * x[j] with s^j read from the multiplied-out table (one coalesced 256-bit read).
-__global__ void coset_scale_direct_kernel(uint4* __restrict__ data, unsigned long long n, int log_n,
-                                          const uint4* __restrict__ table, const __grid_constant__ FieldParams f) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  u32 x[8], w[8];
-  ld_global_256(x, data + 2 * i);
-  ld_global_256(w, table + 2 * (i & ((1ull << log_n) - 1ull)));
-  mul_by(x, w, f);
-  canonicalize(x, f);
-  st_global_256(data + 2 * i, x);
-}
-
-// out[i] = c * in[i]  (c Montgomery-form constant): scaled copies of small tables.
-// shoup != 0: both tables hold 64-byte (w, wq) entries; c stays a Montgomery-form constant, and
-// montmul(c R, w) = c*w is already the plain product.
-__global__ void table_scale_kernel(uint4* __restrict__ out, const uint4* __restrict__ in, unsigned long long count,
-                                   const __grid_constant__ FieldParams f, const __grid_constant__ Fe c, int shoup,
-                                   const __grid_constant__ Fe r2, const __grid_constant__ Fe pinv) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  u32 x[8];
-  ld_global_256(x, in + (shoup ? 4 : 2) * i);
-  mul_by(x, c.v, f);
-  canonicalize(x, f);
-  if (shoup)
-    st_shoup_entry(out + 4 * i, x, r2.v, pinv.v, f);
-  else
-    st_global_256(out + 2 * i, x);
+  ntt_pass_body<1, SH, FZ>(data_in, data_out, A, smem);
 }
 
 }  // namespace ntt256

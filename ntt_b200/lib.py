@@ -26,7 +26,7 @@ EXPORTS = [
     "ntt256_mgpu_create", "ntt256_mgpu_forward", "ntt256_mgpu_inverse", "ntt256_mgpu_forward_batch",
     "ntt256_mgpu_synchronize", "ntt256_mgpu_destroy",
     "ntt256_vec_mul", "ntt256_to_montgomery", "ntt256_from_montgomery", "ntt256_coset_forward",
-    "ntt256_coset_inverse",
+    "ntt256_coset_inverse", "ntt256_forward_mul", "ntt256_inverse_mul", "ntt256_ctx_set_fused_companions", "ntt256_ctx_set_dense_pass4",
     "ntt256_plan_describe", "ntt256_plan_describe_ex", "ntt256_plan_describe_fourstep", "ntt256_launch_count", "ntt256_strerror", "ntt256_last_cuda_error",
     "ntt256_version",
 ]
@@ -82,6 +82,10 @@ def lib() -> ctypes.CDLL:
             getattr(L, name).argtypes = [vp, vp, ctypes.c_ulonglong, vp]
         for name in ("ntt256_coset_forward", "ntt256_coset_inverse"):
             getattr(L, name).argtypes = [vp, vp, ci, ci, u32p, vp]
+        for name in ("ntt256_forward_mul", "ntt256_inverse_mul"):
+            getattr(L, name).argtypes = [vp, vp, vp, ci, ci, vp]
+        L.ntt256_ctx_set_fused_companions.argtypes = [vp, ci]
+        L.ntt256_ctx_set_dense_pass4.argtypes = [vp, ci]
         L.ntt256_enable_peer_access.argtypes = [ci, ci]
         L.ntt256_mgpu_create.argtypes = [ctypes.POINTER(vp), ci, ctypes.POINTER(ci), ci, ci]
         L.ntt256_mgpu_forward.argtypes = [vp, ctypes.POINTER(vp), ci]

@@ -30,8 +30,28 @@ for mont in (False, True):
     print(json.dumps(dict(op="vec_mul", mont_form=mont, n=n, ms=round(ms, 4), gelem_s=round(n / ms / 1e6, 2), hbm_gbs=round(gbs, 1), hbm_frac=round(gbs / peak, 3))))
 ms = timeit(lambda: ctx.to_montgomery(a))
 print(json.dumps(dict(op="to_montgomery", n=n, ms=round(ms, 4), hbm_gbs=round(n * 64 / ms / 1e6, 1), hbm_frac=round(n * 64 / ms / 1e6 / peak, 3))))
-f = timeit(lambda: ctx.forward(a, 24)); c = timeit(lambda: ctx.coset_forward(a, 24, g))
-print(json.dumps(dict(op="coset_forward_2^24", ms=round(c, 4), plain_forward_ms=round(f, 4))))
+f = timeit(lambda: ctx.forward(a, 24)); fi = timeit(lambda: ctx.inverse(a, 24))
+ctx.to_montgomery(b)
+for fused in (True, False):
+    ctx.set_fused_companions(fused)
+    c = timeit(lambda: ctx.coset_forward(a, 24, g)); ci = timeit(lambda: ctx.coset_inverse(a, 24, g))
+    fm = timeit(lambda: ctx.forward_mul(a, b, 24)); im = timeit(lambda: ctx.inverse_mul(a, b, 24))
+    print(json.dumps(dict(op="companions_2^24", fused=fused, coset_forward_ms=round(c, 4), coset_inverse_ms=round(ci, 4),
+                          forward_mul_ms=round(fm, 4), inverse_mul_ms=round(im, 4), plain_forward_ms=round(f, 4),
+                          plain_inverse_ms=round(fi, 4), coset_forward_over_plain=round(c / f, 4),
+                          forward_mul_over_plain=round(fm / f, 4))))
+ctx.set_fused_companions(True)
+# small transforms: the fused forms save a launch and an HBM/L2 round trip
+for log_n, batch in ((20, 1), (16, 1), (16, 16), (12, 64)):
+    m = batch << log_n
+    aa, bb = a[: 8 * m], b[: 8 * m]
+    row = dict(op="companions_small", log_n=log_n, batch=batch, plain_forward_us=round(1e3 * timeit(lambda: ctx.forward(aa, log_n, batch), 30), 2))
+    for fused in (True, False):
+        ctx.set_fused_companions(fused)
+        row["coset_forward_us_" + ("fused" if fused else "separate")] = round(1e3 * timeit(lambda: ctx.coset_forward(aa, log_n, g, batch=batch), 30), 2)
+        row["forward_mul_us_" + ("fused" if fused else "separate")] = round(1e3 * timeit(lambda: ctx.forward_mul(aa, bb, log_n, batch=batch), 30), 2)
+    print(json.dumps(row))
+ctx.set_fused_companions(True)
 del a, b, out
 # pipelined host batches: 256 x 2^16 (config 3 of BASELINE.json) through the host entry point
 log_n, batch = 16, 256

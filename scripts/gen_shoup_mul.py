@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """Generator + limb-exact model of shoup_mul() (ntt_b200/csrc/field_shoup.cuh).
 
-shoup_mul computes  r = x*w mod p  (lazy: r in [0, 2p))  for a TABLE CONSTANT w whose companion
+shoup_mul computes  r = x*w mod p  (lazy: r in [0, 2p + 2^192))  for a TABLE CONSTANT w whose companion
 w' = floor(w * 2^256 / p) is stored next to it (Shoup / Barrett with a per-constant quotient):
 
     q  = floor( (sum over i+j >= 6 of x_i * w'_j * 2^(32(i+j))) / 2^256 )      43 wide MACs
     r  = low 256 bits of  x*w + q*(2^256 - p)                                  56 wide MACs + 16 low MACs
-    if r >= 2p: r -= p                                                          (exact, 17 ALU instructions)
+    if top 64 bits of r > top 64 bits of 2p: r -= p                             (2 compares + 8 predicated adds of 2^256 - p)
 
 q is floor(x*w'/2^256) or one less (the dropped columns sum to < 2^227), so x*w - q*p lies in
 [0, p*(2 + x/2^256)) -- below 3p < 2^256 whenever p < 2^254, which is what makes the low 256 bits the
@@ -185,12 +185,12 @@ def run(pr: Prog, outs, x: int, w: int, wq: int, p: int):
 
 
 def shoup_mul_model(x: int, w: int, p: int):
-    """Returns (r, r_before_correction, q): r = x*w mod p in [0, 2p), computed limb by limb exactly
+    """Returns (r, r_before_correction, q): r = x*w mod p in [0, 2p + 2^192), computed limb by limb exactly
     as the CUDA code does."""
     wq = (w << 256) // p
     pr, outs = _PROG
     r0, v = run(pr, outs, x, w, wq, p)
-    r = r0 - p if r0 >= 2 * p else r0  # step 3 (the CUDA code compares by a borrow chain)
+    r = r0 - p if (r0 >> 192) > ((2 * p) >> 192) else r0  # step 3: the comparison only looks at the top 64 bits
     return r, r0, v
 
 
@@ -221,7 +221,7 @@ def emit_cuda() -> str:
     w("// GENERATED by scripts/gen_shoup_mul.py -- do not edit; the same instruction list is the Python model")
     w("// that tests/test_field_model.py checks against big-integer arithmetic.")
     w("//")
-    w("// shoup_mul(r, x, w, wq, f):  r = x*w mod p, r in [0, 2p), for a table constant w < p with its")
+    w("// shoup_mul(r, x, w, wq, f):  r = x*w mod p, r in [0, 2p + 2^192), for a table constant w < p with its")
     w("// companion wq = floor(w * 2^256 / p).  x is any 256-bit value.  Needs p < 2^254 (3p < 2^256).")
     w(f"// {n_wide} wide (32x32->64) multiplies + {n_lo_only} low ones, against 128 + 8 of the Montgomery product in")
     w("// field.cuh: the wide multiply is what the fmaheavy pipe of B200 is short of (4 cycles per warp).")
@@ -242,23 +242,20 @@ def emit_cuda() -> str:
             w(f"  fn::{fnname}({d}, {_operand(a)}, {_operand(b)}, {_operand(c if c is not None else 0)});")
         else:
             w(f"  fn::{fnname}({d}, {_operand(a)}, {_operand(b)});")
-    w("  // step 3: r in [0, 3p) -> [0, 2p): subtract p when r >= 2p (borrow chain of r - 2p, then a predicated chain)")
-    w("  u32 bw, dz;")
-    for k in range(8):
-        fnname = "sub_cc" if k == 0 else "subc_cc"
-        w(f"  fn::{fnname}(dz, {outs[k]}, f.p2[{k}]);")
-    w("  fn::subc(bw, 0u, 0u);  // 0xffffffff: r < 2p, keep")
-    w("  (void)dz;")
+    w("  // step 3: r in [0, 3p) -> [0, 2p + 2^192): subtract p (add 2^256 - p) when the top 64 bits of r exceed those")
+    w("  // of 2p -- then r >= 2p for certain; otherwise r < 2p + 2^192 (the wide-lazy range of field_wl.cuh)")
     args_out = ", ".join(f'"+r"({outs[k]})' for k in range(8))
-    args_in = ", ".join(f'"r"(f.p[{k}])' for k in range(8))
-    w('  asm volatile("{\\n\\t.reg .pred q;\\n\\t"')
-    w('      "setp.eq.u32 q, %8, 0;\\n\\t"')
+    args_in = ", ".join(f'"r"(f.pbar[{k}])' for k in range(8))
+    w('  asm volatile("{\\n\\t.reg .pred q;\\n\\t.reg .u64 a, b;\\n\\t"')
+    w('      "mov.b64 a, {%6, %7};\\n\\t"')
+    w('      "mov.b64 b, {%16, %17};\\n\\t"')
+    w('      "setp.gt.u64 q, a, b;\\n\\t"')
     for k in range(8):
-        ins = "sub.cc.u32 " if k == 0 else ("subc.u32   " if k == 7 else "subc.cc.u32")
-        w(f'      "@q {ins} %{k}, %{k}, %{9 + k};\\n\\t"')
+        ins = "add.cc.u32 " if k == 0 else ("addc.u32   " if k == 7 else "addc.cc.u32")
+        w(f'      "@q {ins} %{k}, %{k}, %{8 + k};\\n\\t"')
     w('      "}"')
     w(f"      : {args_out}")
-    w(f'      : "r"(bw), {args_in});')
+    w(f'      : {args_in}, "r"(f.p2[6]), "r"(f.p2[7]));')
     for k in range(8):
         w(f"  r[{k}] = {outs[k]};")
     w("}")

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include "../ntt_b200/csrc/field.cuh"
 #include "../ntt_b200/csrc/field_shoup.cuh"
+#include "../ntt_b200/csrc/field_wl.cuh"
 #include "shoup_testvec.h"
 
 using namespace ntt256;
@@ -30,7 +31,7 @@ __global__ void k_check(const u32* __restrict__ vec, int n, const __grid_constan
     want[k] = vec[(i * 5 + 4) * 8 + k];
   }
   shoup_mul(r1, x, w, wq, f);
-  canonicalize(r1, f);
+  canonicalize_wl(r1, f);
   mont_mul(r2, wm, x, f);
   canonicalize(r2, f);
   int b1 = 0, b2 = 0;
@@ -93,8 +94,13 @@ __global__ void __launch_bounds__(256) k_bfly(u32* out, const u32* in, const __g
 #pragma unroll
     for (int n = 0; n < N; ++n) {
       u32 s[8], d[8], r[8];
-      add_lazy(s, x[n], y[n], f);
-      sub_lazy(d, x[n], y[n], f);
+      if (MODE == 2) {  // wide-lazy policy (field_wl.cuh)
+        add_wl(s, x[n], y[n], f);
+        sub_wl_mul(d, x[n], y[n], f);
+      } else {
+        add_lazy(s, x[n], y[n], f);
+        sub_lazy(d, x[n], y[n], f);
+      }
       if (MODE) shoup_mul(r, d, w, wq, f); else mont_mul(r, w, d, f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) { x[n][k] = s[k]; y[n][k] = r[k]; }
@@ -154,6 +160,15 @@ int main(int argc, char** argv) {
     u64 d = (u64)0 - (u64)p[k] - bw;  // 2^256 - p, limb by limb
     f.pbar[k] = (u32)d; bw = (p[k] != 0 || bw) ? 1 : 0;
   }
+  {
+    u64 b2 = 0, c2 = 0;
+    for (int k = 0; k < 8; ++k) {
+      u64 d = (u64)0 - (u64)f.p2[k] - b2;  // 2^256 - 2p
+      f.p2bar[k] = (u32)d; b2 = (f.p2[k] != 0 || b2) ? 1 : 0;
+      u64 t = (u64)f.p2[k] + (u64)p[k] + c2;  // 3p
+      f.kp[k] = (u32)t; c2 = t >> 32;
+    }
+  }
   f.np0 = 0xefffffffu;
 
   k_check<<<(kNumVec + 127) / 128, 128>>>(d_in, kNumVec, f, d_bad);
@@ -175,6 +190,8 @@ int main(int argc, char** argv) {
     printf("{\"test\": \"butterfly_mont_x4\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"G_per_s\": %.2f, \"smsp_clk_per_warp_op\": %.1f}\n", occ, ms, tot / ms / 1e6, ms * cyc);
     ms = best_ms([&] { k_bfly<4, 1><<<blocks, threads>>>(d_out, d_in, f, iters); });
     printf("{\"test\": \"butterfly_shoup_x4\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"G_per_s\": %.2f, \"smsp_clk_per_warp_op\": %.1f}\n", occ, ms, tot / ms / 1e6, ms * cyc);
+    ms = best_ms([&] { k_bfly<4, 2><<<blocks, threads>>>(d_out, d_in, f, iters); });
+    printf("{\"test\": \"butterfly_shoup_widelazy_x4\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"G_per_s\": %.2f, \"smsp_clk_per_warp_op\": %.1f}\n", occ, ms, tot / ms / 1e6, ms * cyc);
   }
   return 0;
 }

@@ -18,9 +18,30 @@ def _brev(v: int, bits: int) -> int:
     return r
 
 
+class ExactArith:
+    """Field operations of the model: exact residues.  tests/wl_model.py substitutes the limb-level
+    wide-lazy policy of Shoup contexts (field_wl.cuh + field_shoup.cuh) to check its ranges."""
+
+    def __init__(self, p: int):
+        self.p = p
+
+    def add(self, a, b):
+        return (a + b) % self.p
+
+    def sub(self, a, b, to_mul):
+        return (a - b) % self.p
+
+    def mul(self, x, w):
+        return x * w % self.p
+
+    def canon(self, x):
+        return x % self.p
+
+
 def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inverse: bool = False,
-             scale: int | None = None, peer: dict | None = None, group_bits: int = 3) -> None:
+             scale: int | None = None, peer: dict | None = None, group_bits: int = 3, arith=None) -> None:
     """In-place simulation of one pass over one transform (len(data) = 2^(T + nblk_bits))."""
+    A = arith or ExactArith(p)
     T, d = pd["T"], pd["d"]
     lowp = T - d
     GB = group_bits
@@ -52,9 +73,12 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
                 else:
                     x = [tile[l] for l in lams]
 
-                def bfly(i, j):
+                def bfly(i, j, to_mul):
                     a, b = x[i], x[j]
-                    x[i], x[j] = (a + b) % p, (a - b) % p
+                    x[i], x[j] = A.add(a, b), A.sub(a, b, to_mul)
+
+                # what the kernel's tail_mul says: every element with a processed bit set meets a product next
+                tail_mul = (not last) or bool(pd["has_tw"]) or (scale is not None and bool(pd.get("scale_out")))
 
                 w8 = lambda k: root(k * (N // 8))
                 for k in range(nb):  # DIF stages on the top nb bits of the group, top bit first
@@ -62,11 +86,11 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
                     for u in range(NE):
                         if u & (1 << bit):
                             continue
-                        bfly(u, u | (1 << bit))
                         t = (u >> (GB - nb)) & ((1 << (nb - 1 - k)) - 1)
                         e8 = t << (3 - (nb - k))
+                        bfly(u, u | (1 << bit), e8 != 0 or (k == nb - 1 and tail_mul))
                         if e8:
-                            x[u | (1 << bit)] = x[u | (1 << bit)] * w8(e8) % p
+                            x[u | (1 << bit)] = A.mul(x[u | (1 << bit)], w8(e8))
                 if not last:
                     pb = sb + GB - nb
                     m = sb + GB - lowp
@@ -82,9 +106,8 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
                         if uproc != 0 or fold:
                             tl = (tl0 | (rest << ush)) & tl_mask
                             e = ((tl * v) << sh) & ((1 << loc_bits) - 1)
-                            x[u] = x[u] * root(e * (N >> loc_bits)) % p
-                            if fold:
-                                x[u] = x[u] * scale % p
+                            w = root(e * (N >> loc_bits))
+                            x[u] = A.mul(x[u], w * scale % p if fold else w)
                     for u in range(NE):
                         tile[lams[u]] = x[u]
                 else:
@@ -95,9 +118,11 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
                             khi = _brev(lams[u] >> lowp, d) if d else 0
                             jl = jl0 + sum(gw[i] for i in range(GB) if (u >> i) & 1)
                             e = ((jl * khi) << pd["tw_lshift"]) & (N - 1)
-                            x[u] = x[u] * root(e) % p
+                            x[u] = A.mul(x[u], root(e))
                     if scale is not None and pd.get("scale_out"):
-                        x = [v * scale % p for v in x]
+                        x = [A.mul(v, scale) for v in x]
+                    if pd.get("is_final"):
+                        x = [A.canon(v) for v in x]
                     for u in range(NE):
                         stores.append((base + _deposit(lams[u], pd["out_pos"], T), x[u]))
             for pos, val in stores:
@@ -109,7 +134,7 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
                     peer["recv"][dest][roff] = val
 
 
-def run_plan(data: list[int], plan: dict, p: int, g: int, max_log_n: int, inverse: bool = False) -> list[int]:
+def run_plan(data: list[int], plan: dict, p: int, g: int, max_log_n: int, inverse: bool = False, arith=None) -> list[int]:
     out = list(data)
     w_max = pow(g, (p - 1) >> max_log_n, p)
     n = len(out)
@@ -123,5 +148,5 @@ def run_plan(data: list[int], plan: dict, p: int, g: int, max_log_n: int, invers
                 pd["scaled_round"] = 0  # 1/n folded into the first round's twiddle table
             else:
                 pd["scale_out"] = 1
-        run_pass(out, pd, p, w_max, max_log_n, inverse, scale, group_bits=plan.get("group_bits", 3))
+        run_pass(out, pd, p, w_max, max_log_n, inverse, scale, group_bits=plan.get("group_bits", 3), arith=arith)
     return out

@@ -531,6 +531,89 @@ def test_coset_transforms(torch_cuda, ctxs, log_n, batch):
         assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 8), x)
 
 
+@pytest.mark.parametrize("field", ["bn254_fr", "bls12_381_fr"])
+def test_fused_and_separate_companions_agree_and_match_the_oracle(torch_cuda, field):
+    """Coset shift inside the first pass / s^-k inside the last pass / pointwise product inside the last pass
+    (ntt256_ctx_set_fused_companions) against the separate element-wise kernels and against Python integers;
+    sizes that run on the 2-, 4- and 8-elements-per-thread kernels, batches, one- and multi-pass plans."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS[field]
+    R = (1 << 256) % p
+    ctx = Ntt256(field, max_log_n=22)
+    try:
+        for log_n, batch in ((3, 5), (8, 3), (12, 2), (16, 1), (17, 2), (18, 1), (21, 1)):
+            n = 1 << log_n
+            shift = pow(g, 3, p) if log_n % 2 else 0x1234567890ABCDEF1234567890ABCDEF % p
+            x = co.splitmix_elements(n * batch, p, 4000 + log_n)
+            b = co.splitmix_elements(n * batch, p, 5000 + log_n)
+            d0 = torch.from_numpy(x.view(np.int32)).cuda().view(-1)
+            bm = torch.from_numpy(b.view(np.int32)).cuda().view(-1)
+            ctx.to_montgomery(bm)
+            outs = {}
+            ctx.coset_forward(d0.clone(), log_n, shift, batch=batch)  # builds the shift tables (counted launches)
+            ctx.coset_inverse(d0.clone(), log_n, shift, batch=batch)
+            for fused in (True, False):
+                ctx.set_fused_companions(fused)
+                before = ctx.launch_count
+                d = d0.clone()
+                ctx.coset_forward(d, log_n, shift, batch=batch)
+                cf = d.clone()
+                ctx.coset_inverse(d, log_n, shift, batch=batch)
+                torch.cuda.synchronize()
+                assert torch.equal(d, d0), (field, log_n, fused)
+                d = d0.clone()
+                ctx.forward_mul(d, bm, log_n, batch=batch)
+                fm = d.clone()
+                d = d0.clone()
+                ctx.inverse_mul(d, bm, log_n, batch=batch)
+                torch.cuda.synchronize()
+                outs[fused] = (cf.cpu().numpy(), fm.cpu().numpy(), d.cpu().numpy(), ctx.launch_count - before)
+            for k in range(3):
+                assert np.array_equal(outs[True][k], outs[False][k]), (field, log_n, k)
+            assert outs[True][3] < outs[False][3]  # the fused path really launches fewer kernels
+            if log_n <= 16:
+                xi, bi = co.array_to_ints(x), co.array_to_ints(b)
+                pw = [1] * n
+                for j in range(1, n):
+                    pw[j] = pw[j - 1] * shift % p
+                scaled = co.ints_to_array([xi[t * n + j] * pw[j] % p for t in range(batch) for j in range(n)])
+                want_cf = np.concatenate([co.ntt(scaled[t * n:(t + 1) * n], p, g, threads=4) for t in range(batch)])
+                assert np.array_equal(outs[True][0].view(np.uint32).reshape(-1, 8), want_cf)
+                fw = np.concatenate([co.ntt(x[t * n:(t + 1) * n], p, g, threads=4) for t in range(batch)])
+                want_fm = [v * w % p for v, w in zip(co.array_to_ints(fw), bi)]
+                assert co.array_to_ints(outs[True][1].view(np.uint32).reshape(-1, 8)) == want_fm
+    finally:
+        ctx.close()
+
+
+def test_fused_coset_with_the_montgomery_twiddle_mode(torch_cuda):
+    """BN254 contexts default to Shoup twiddles; the fused companions must also work with 32-byte tables."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = Ntt256("bn254_fr", max_log_n=18)
+    try:
+        x = co.splitmix_elements(1 << 14, p, 99)
+        res = []
+        for mode in (True, False):
+            ctx.set_twiddle_mode(mode)
+            d = torch.from_numpy(x.view(np.int32)).cuda().view(-1)
+            ctx.coset_forward(d, 14, g)
+            torch.cuda.synchronize()
+            res.append(d.cpu().numpy())
+            ctx.coset_inverse(d, 14, g)
+            torch.cuda.synchronize()
+            assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 8), x)
+        assert np.array_equal(res[0], res[1])
+    finally:
+        ctx.close()
+
+
 def test_pipelined_host_batches(torch_cuda, ctxs):
     """Host-buffer entry point with a batch large enough to be streamed in chunks (3-slot ring,
     uplink / kernels / downlink on separate streams): same bits as transform-by-transform."""
