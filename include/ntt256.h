@@ -75,6 +75,13 @@ int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits);
  * (default: 1/16 of the device's memory, i.e. every n <= 2^28 on a 180 GB B200; when the
  * allocation fails the two-lookup path is used); 0 selects the two-lookup path always. */
 int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes);
+/* All streamed arrays of a context together stay below total_bytes (default: 1/8 of the device's memory):
+ * before a new one is built the least recently used ones are freed (cudaFree waits for the device, so a
+ * launch that still reads one is never cut off); a transform whose array was dropped rebuilds it at its
+ * next call.  ntt256_ctx_table_bytes returns the device memory the context holds in twiddle / coset
+ * tables right now and, through *streamed_bytes (may be NULL), the streamed arrays' share of it. */
+int ntt256_ctx_set_stream_twiddle_budget(ntt256_ctx* ctx, size_t total_bytes);
+size_t ntt256_ctx_table_bytes(const ntt256_ctx* ctx, size_t* streamed_bytes);
 /* Calls with batch * 2^log_n <= max_elements (default 2^17) are latency-bound and run on the
  * four-elements-per-thread kernel, those of at most half that on the two-elements-per-thread
  * kernel (more, shorter threads); 0 keeps every call on the throughput kernel. */

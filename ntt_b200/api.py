@@ -129,6 +129,16 @@ class Ntt256:
         """Largest streamed first-pass twiddle array built automatically (0: always two lookups)."""
         self._check(self._L.ntt256_ctx_set_stream_twiddle_limit(self._h, max_bytes))
 
+    def set_stream_twiddle_budget(self, total_bytes: int):
+        """All streamed twiddle arrays together stay below this; least recently used ones are dropped first."""
+        self._check(self._L.ntt256_ctx_set_stream_twiddle_budget(self._h, total_bytes))
+
+    def table_bytes(self) -> tuple:
+        """(device bytes held in twiddle / coset tables, of which streamed first-pass arrays)."""
+        st = ctypes.c_size_t(0)
+        tot = int(self._L.ntt256_ctx_table_bytes(self._h, ctypes.byref(st)))
+        return tot, int(st.value)
+
     @property
     def launch_count(self) -> int:
         return int(self._L.ntt256_launch_count(self._h))

@@ -73,9 +73,18 @@ struct ntt256_ctx {
   int fuse_companions = -1;
   std::map<int, uint4*> loc_scaled;       // log_n -> (1/n) * loc[] : folds the inverse scaling into a round twiddle
   // streamed pass-twiddle arrays, keyed by (plan id, pass index, direction)
-  std::map<std::tuple<unsigned long long, int, int>, uint4*> tw_streams;
+  struct TwStream {
+    uint4* tab = nullptr;
+    size_t bytes = 0;
+    unsigned long long last_use = 0;  // value of tw_clock at the last launch that read it
+  };
+  std::map<std::tuple<unsigned long long, int, int>, TwStream> tw_streams;
   size_t tw_stream_limit = (size_t)1 << 30;   // largest array built automatically (bytes); 0 = never;
                                               // set to 1/16 of the device's memory at creation
+  size_t tw_stream_budget = (size_t)2 << 30;  // all cached arrays together; least recently used ones are dropped
+                                              // to make room (set to 1/8 of the device's memory at creation)
+  size_t tw_stream_bytes = 0;
+  unsigned long long tw_clock = 0;
   unsigned long long next_plan_id = 1;
   struct CosetTables {
     U256 shift;
@@ -158,6 +167,25 @@ int build_power_table(ntt256_ctx* ctx, uint4** out, const U256& base_mont, int b
   return NTT256_OK;
 }
 
+void drop_tw_streams(ntt256_ctx* ctx) {
+  for (auto& kv : ctx->tw_streams) cudaFree(kv.second.tab);
+  ctx->tw_streams.clear();
+  ctx->tw_stream_bytes = 0;
+}
+
+// Make room for a new streamed twiddle array of `need` bytes: least recently used arrays go first.  cudaFree
+// waits for the device, so an array still being read by an earlier launch is not pulled from under it.
+void evict_tw_streams(ntt256_ctx* ctx, size_t need) {
+  while (!ctx->tw_streams.empty() && ctx->tw_stream_bytes + need > ctx->tw_stream_budget) {
+    auto victim = ctx->tw_streams.begin();
+    for (auto it = ctx->tw_streams.begin(); it != ctx->tw_streams.end(); ++it)
+      if (it->second.last_use < victim->second.last_use) victim = it;
+    cudaFree(victim->second.tab);
+    ctx->tw_stream_bytes -= victim->second.bytes;
+    ctx->tw_streams.erase(victim);
+  }
+}
+
 void free_twiddle_tables(ntt256_ctx* ctx) {
   if (ctx->om_hi) cudaFree(ctx->om_hi);
   if (ctx->om_lo) cudaFree(ctx->om_lo);
@@ -165,8 +193,7 @@ void free_twiddle_tables(ntt256_ctx* ctx) {
   ctx->om_hi = ctx->om_lo = ctx->loc = nullptr;
   for (auto& kv : ctx->loc_scaled) cudaFree(kv.second);
   ctx->loc_scaled.clear();
-  for (auto& kv : ctx->tw_streams) cudaFree(kv.second);
-  ctx->tw_streams.clear();
+  drop_tw_streams(ctx);
 }
 
 // The three w_N power tables of the pass kernels, in the context's twiddle representation.
@@ -395,11 +422,12 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
     A.tw_gen_out = nullptr;
     if (A.pd.has_tw && A.pd.tw_lshift < ctx->lo_bits && ctx->tw_stream_limit > 0) {
       const size_t tbytes = (size_t)(sh ? 64 : 32) << (A.pd.T + A.pd.nblk_bits);
-      if (tbytes <= ctx->tw_stream_limit) {
+      if (tbytes <= ctx->tw_stream_limit && tbytes <= ctx->tw_stream_budget) {
         auto tkey = std::make_tuple(plan.id, (int)i, inverse ? 1 : 0);
         auto ts = ctx->tw_streams.find(tkey);
         if (ts == ctx->tw_streams.end()) {
           uint4* tab = nullptr;
+          evict_tw_streams(ctx, tbytes);
           if (cudaMalloc((void**)&tab, tbytes) == cudaSuccess) {
             PassArgs G = A;
             G.tw_gen_out = tab;
@@ -413,12 +441,19 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
             CTX_CUDA(cudaGetLastError());
             // one-off: the array may be read from other streams by later calls
             CTX_CUDA(cudaStreamSynchronize(stream));
-            ts = ctx->tw_streams.emplace(tkey, tab).first;
+            ntt256_ctx::TwStream rec;
+            rec.tab = tab;
+            rec.bytes = tbytes;
+            ts = ctx->tw_streams.emplace(tkey, rec).first;
+            ctx->tw_stream_bytes += tbytes;
           } else {
             cudaGetLastError();  // not enough memory: keep the two-lookup path
           }
         }
-        if (ts != ctx->tw_streams.end()) A.tw_stream = ts->second;
+        if (ts != ctx->tw_streams.end()) {
+          ts->second.last_use = ++ctx->tw_clock;
+          A.tw_stream = ts->second.tab;
+        }
       }
     }
     if (peer && i + 1 == plan.passes.size()) {
@@ -820,7 +855,10 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
     // a streamed first-pass twiddle array is as large as the transform itself; allow each one 1/16
     // of the device (11 GiB on a 180 GB B200: every size up to 2^28)
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) ctx->tw_stream_limit = total_b / 16;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) {
+      ctx->tw_stream_limit = total_b / 16;
+      ctx->tw_stream_budget = total_b / 8;
+    }
   }
   const int big = 32 << kMaxTileBits, small = 32 << 11;
   if (!pass_inst_set_smem<false, false>(big, small) || !pass_inst_set_smem<false, true>(big, small) ||
@@ -879,8 +917,7 @@ int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits) {
   ctx->coalesce_bits = coalesce_bits;
   ctx->auto_tile = false;
   ctx->plans.clear();
-  for (auto& kv : ctx->tw_streams) cudaFree(kv.second);
-  ctx->tw_streams.clear();
+  drop_tw_streams(ctx);
   return NTT256_OK;
 }
 
@@ -1021,7 +1058,9 @@ static int fourstep(ntt256_ctx* ctx, int kind, void* d_shard, int log_n, int log
   CTX_CUDA(cudaSetDevice(ctx->device));
   const Plan* plan = nullptr;
   // step 2 does not depend on the rank (no foreign time bits remain)
-  int rc = get_plan(ctx, PlanKey{kind, log_n, log_r, log_p, first_step ? rank : 0}, &plan);
+  PlanKey key{kind, log_n, log_r, log_p, first_step ? rank : 0};
+  if (ctx->force_group_bits) key.group_bits = ctx->force_group_bits;
+  int rc = get_plan(ctx, key, &plan);
   if (rc) return rc;
   // ranks armed with ntt256_ctx_set_peer_sync: step 1 with peer stores ends by publishing a new epoch,
   // step 2 begins by waiting for it (from every rank)
@@ -1243,9 +1282,30 @@ int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   ctx->tw_stream_limit = max_bytes;
-  for (auto& kv : ctx->tw_streams) cudaFree(kv.second);
-  ctx->tw_streams.clear();
+  drop_tw_streams(ctx);
   return NTT256_OK;
+}
+
+int ntt256_ctx_set_stream_twiddle_budget(ntt256_ctx* ctx, size_t total_bytes) {
+  if (!ctx) return NTT256_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ctx->tw_stream_budget = total_bytes;
+  evict_tw_streams(ctx, 0);
+  return NTT256_OK;
+}
+
+size_t ntt256_ctx_table_bytes(const ntt256_ctx* ctx, size_t* streamed_bytes) {
+  if (!ctx) return 0;
+  const size_t e = ctx->shoup ? 64 : 32;
+  size_t fixed = ((size_t)e << ctx->hi_bits) + ((size_t)e << ctx->lo_bits) + ((size_t)e << ctx->loc_bits);
+  fixed += ctx->loc_scaled.size() * ((size_t)e << ctx->loc_bits);
+  size_t coset = 0;
+  for (auto& c : ctx->cosets) {
+    coset += (size_t)64 << c.lo_bits;  // two factored tables
+    if (c.direct) coset += (size_t)(c.direct_shoup ? 64 : 32) << c.log_n;
+  }
+  if (streamed_bytes) *streamed_bytes = ctx->tw_stream_bytes;
+  return fixed + coset + ctx->tw_stream_bytes;
 }
 
 int ntt256_ctx_set_peer_sync(ntt256_ctx* ctx, void* const* flag_bufs, int nranks, int rank, double timeout_s) {

@@ -653,6 +653,36 @@ def test_streamed_and_two_lookup_twiddles_agree(torch_cuda):
     ctx.close()
 
 
+def test_streamed_twiddle_arrays_stay_within_their_budget(torch_cuda):
+    """The streamed first-pass arrays are as large as the transform (per size and direction): with a budget of
+    one 2^20 array the least recently used ones are dropped and rebuilt on demand, the bits never change, and
+    the context reports what it holds."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    p, g = FIELDS["bls12_381_fr"]
+    ctx = Ntt256("bls12_381_fr", max_log_n=21)
+    one = 32 << 20
+    ctx.set_stream_twiddle_budget(one + (one >> 1))  # room for 2^20 alone, or for 2^19 + one more 2^19
+    xs = {L: co.splitmix_elements(1 << L, p, 900 + L) for L in (19, 20)}
+    want = {L: co.ntt(xs[L], p, g, threads=8) for L in (19, 20)}
+    seen = set()
+    for L, inverse in ((19, False), (19, True), (20, False), (19, False), (20, True), (20, False), (19, True)):
+        if inverse:
+            assert np.array_equal(_gpu_forward(torch_cuda, ctx, want[L], L, inverse=True), xs[L]), (L, inverse)
+        else:
+            assert np.array_equal(_gpu_forward(torch_cuda, ctx, xs[L], L), want[L]), (L, inverse)
+        total, streamed = ctx.table_bytes()
+        assert 0 < streamed <= one + (one >> 1), (L, inverse, streamed)
+        assert total > streamed
+        seen.add(streamed)
+    assert len(seen) > 1  # arrays really came and went
+    ctx.set_stream_twiddle_budget(0)
+    assert ctx.table_bytes()[1] == 0
+    assert np.array_equal(_gpu_forward(torch_cuda, ctx, xs[19], 19), want[19])  # two-lookup path when nothing fits
+    ctx.close()
+
+
 def test_zero_copy_host_buffers(torch_cuda, ctxs):
     """Pinned host buffers: the first pass reads host memory and the last pass writes it directly
     (no staging copies).  Distinct and aliased in/out buffers, one pass and several passes."""
