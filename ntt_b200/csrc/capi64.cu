@@ -1,0 +1,728 @@
+// C ABI of the 64-bit transforms (include/ntt64.h): the reference's `bits` template parameter
+// (/root/reference/src/big-num.cu:57,67,172,260) at 64 -- the width its own CPU NTT runs in (big-num.cu:37-55).
+// Same planner as the wide libraries (plan.cpp), kernels ntt_kernels_64.cuh, field layer field64.cuh.
+// Host side: field constants and table seeds (64-bit modular arithmetic on unsigned __int128), plan and kernel
+// shape by call size, device tables built on the device, 1/n folded into a round-twiddle table, coset shifts
+// fused into the end passes, pipelined host-buffer batches.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/ntt64.h"
+#include "ntt_kernels_64.cuh"
+#include "plan.h"
+
+using namespace ntt64;
+using ntt256::Plan;
+using ntt256::PlanRequest;
+using ntt256::make_plan;
+
+namespace {
+
+typedef unsigned __int128 u128;
+constexpr int kTileBits64 = 12;   // 2^12 x 8 B = 32 KiB of shared memory, 256 threads, four CTAs per SM
+constexpr int kCoalesce64 = 4;    // runs of >= 16 elements = 128 bytes
+constexpr int kHiBits64 = 20;     // 2^20 x 8 B = 8 MiB: stays in L2
+constexpr int kLocBits64 = 12;
+constexpr int kMaxTile64 = 14;    // 128 KiB of shared memory, 1024 threads
+constexpr size_t kCosetDirectMax64 = (size_t)256 << 20;  // one multiplied-out shift^j table (2^25 points)
+
+struct HostField64 {
+  u64 p = 0;
+  bool gl = false;
+  u64 np = 0;   // -p^-1 mod 2^64
+  u64 r = 0;    // 2^64 mod p
+  u64 r2 = 0;   // 2^128 mod p
+  void init(u64 P) {
+    p = P;
+    gl = (P == kGoldilocksP);
+    u64 inv = 1;  // Newton: p^-1 mod 2^64
+    for (int i = 0; i < 6; ++i) inv *= 2 - P * inv;
+    np = 0 - inv;
+    r = (u64)(((u128)1 << 64) % P);
+    r2 = (u64)(((u128)r * r) % P);
+  }
+  u64 mul(u64 a, u64 b) const { return (u64)(((u128)a * b) % p); }
+  u64 pow(u64 b, u64 e) const {
+    u64 acc = 1 % p;
+    while (e) {
+      if (e & 1) acc = mul(acc, b);
+      b = mul(b, b);
+      e >>= 1;
+    }
+    return acc;
+  }
+  u64 inv(u64 a) const { return pow(a, p - 2); }
+  // what a twiddle table holds for the plain value w: w itself (Goldilocks) or its Montgomery form w * 2^64
+  u64 tab(u64 w) const { return gl ? w : mul(w, r); }
+};
+
+struct PlanKey64 {
+  int log_n, tile_bits, group_bits, coalesce;
+  bool operator<(const PlanKey64& o) const {
+    return std::tie(log_n, tile_bits, group_bits, coalesce) < std::tie(o.log_n, o.tile_bits, o.group_bits, o.coalesce);
+  }
+};
+
+}  // namespace
+
+struct ntt64_ctx {
+  int device = 0;
+  int max_log_n = 0;
+  HostField64 hf;
+  Params64 fp;
+  u64 wN = 0, wN_inv = 0;  // plain
+  u64 *om_hi = nullptr, *om_lo = nullptr, *loc = nullptr;
+  int hi_bits = 0, lo_bits = 0, loc_bits = 0;
+  u64 c16[2][7];  // table format
+  u64 w4[2];
+  int tile_bits = kTileBits64, coalesce_bits = kCoalesce64;
+  bool auto_shape = true;
+  struct PlanTables {  // per pass: the index tables of PassArgs64 (one device allocation each)
+    std::vector<u32*> thr;
+    std::vector<uint2*> blk;
+  };
+  std::map<PlanKey64, Plan> plans;
+  std::map<PlanKey64, PlanTables> plan_tables;
+  std::map<int, u64*> loc_scaled;  // log_n -> (1/n) * loc[]
+  struct Coset {
+    u64 shift;     // plain
+    int log_n;
+    int with_ninv; // the table carries 1/n as well (inverse coset transforms)
+    u64* direct;   // shift^j (times 1/n), j < 2^log_n, table format; or null (too large)
+    u64 *hi, *lo;  // factored tables when direct is null
+    int lo_bits;
+  };
+  std::vector<Coset> cosets;
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;
+  cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_done[3] = {nullptr, nullptr, nullptr},
+              ev_out[3] = {nullptr, nullptr, nullptr};
+  unsigned long long launches = 0;
+  std::string last_err;
+};
+
+namespace {
+
+#define CTX_CUDA(call)                                                     \
+  do {                                                                     \
+    cudaError_t e_ = (call);                                               \
+    if (e_ != cudaSuccess) {                                               \
+      ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(e_);  \
+      return NTT256_ERR_CUDA;                                              \
+    }                                                                      \
+  } while (0)
+
+u64 pow2k(const HostField64& hf, u64 b, int k) {  // b^(2^k)
+  for (int i = 0; i < k; ++i) b = hf.mul(b, b);
+  return b;
+}
+
+template <bool GL>
+void launch_powers(u64* out, const u64* d_pw, int bits, unsigned long long count, const ntt64_ctx* ctx, u64 one_tab,
+                   cudaStream_t stream) {
+  const int threads = 256;
+  twiddle_powers_kernel64<GL><<<(unsigned)((count + threads - 1) / threads), threads, 0, stream>>>(
+      out, d_pw, bits, count, ctx->fp, one_tab);
+}
+
+// out[i] = start * base^i, i < 2^bits, in table format (start and base plain)
+int build_power_table(ntt64_ctx* ctx, u64** out, u64 base, int bits, u64 start = 1, cudaStream_t stream = 0) {
+  const unsigned long long count = 1ull << bits;
+  *out = nullptr;
+  CTX_CUDA(cudaMalloc((void**)out, count * 8));
+  std::vector<u64> pw(64, 0);
+  u64 b = base;
+  for (int k = 0; k < std::max(bits, 1); ++k) {
+    pw[k] = ctx->hf.tab(b);
+    b = ctx->hf.mul(b, b);
+  }
+  u64* d_pw = nullptr;
+  auto fail = [&](const char* what) {
+    if (d_pw) cudaFree(d_pw);
+    cudaFree(*out);
+    *out = nullptr;
+    ctx->last_err = what;
+    return NTT256_ERR_CUDA;
+  };
+  if (cudaMalloc((void**)&d_pw, pw.size() * 8) != cudaSuccess) return fail("cudaMalloc (power seeds)");
+  if (cudaMemcpyAsync(d_pw, pw.data(), pw.size() * 8, cudaMemcpyHostToDevice, stream) != cudaSuccess)
+    return fail("cudaMemcpy (power seeds)");
+  if (ctx->hf.gl) launch_powers<true>(*out, d_pw, bits, count, ctx, ctx->hf.tab(start), stream);
+  else launch_powers<false>(*out, d_pw, bits, count, ctx, ctx->hf.tab(start), stream);
+  ++ctx->launches;
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) return fail("twiddle_powers_kernel64");
+  cudaFree(d_pw);
+  return NTT256_OK;
+}
+
+// Kernel shape by call size: sixteen elements per thread in 2^12-element tiles for throughput; smaller tiles,
+// then four elements per thread, for calls too small to fill 148 SMs with such CTAs.
+void choose_shape(const ntt64_ctx* ctx, int log_n, int batch, int* tile_bits, int* group_bits, int* coalesce) {
+  int T = std::min(ctx->tile_bits, log_n), gb = 4, g = ctx->coalesce_bits;
+  if (ctx->auto_shape) {
+    const long long E = (long long)batch << log_n;
+    if (E <= (1ll << 15)) {
+      gb = 2;
+      T = std::min(8, log_n);
+      g = 0;
+    } else if (E <= (1ll << 19)) {
+      T = std::min(10, log_n);
+      g = std::min(g, 2);
+    }
+  }
+  if (T < gb) gb = 2;
+  g = std::min(g, T);
+  *tile_bits = T;
+  *group_bits = gb;
+  *coalesce = g;
+}
+
+bool plan_for(int log_n, int T, int gb, int g, int max_log_n, Plan* plan) {
+  PlanRequest req;
+  req.log_n = log_n;
+  req.tile_bits = T;
+  req.coalesce_bits = g;
+  req.max_log_n = max_log_n;
+  req.group_bits = gb;
+  req.max_tile_bits = kMaxTile64;
+  bool ok = make_plan(req, plan);
+  // small tiles with wide coalescing leave too few free tile bits: relax the run length, then allow more
+  // passes, then grow the tile
+  for (int gg = req.coalesce_bits - 1; !ok && gg >= 0; --gg) {
+    req.coalesce_bits = gg;
+    ok = make_plan(req, plan, 12);
+  }
+  for (int t = req.tile_bits + 1; !ok && t <= kMaxTile64; ++t) {
+    req.tile_bits = t;
+    ok = make_plan(req, plan, 12);
+  }
+  return ok;
+}
+
+u32 deposit_host(unsigned long long v, const int8_t* pos, int n) {
+  unsigned long long r = 0;
+  for (int i = 0; i < n; ++i) r |= ((v >> i) & 1ull) << pos[i];
+  return (u32)r;
+}
+u32 swz_host(u32 l) { return l ^ ((l >> 5) & 31u) ^ ((l >> 10) & 31u); }
+
+void free_plan_tables(ntt64_ctx* ctx) {
+  for (auto& kv : ctx->plan_tables) {
+    for (u32* p : kv.second.thr) cudaFree(p);
+    for (uint2* p : kv.second.blk) cudaFree(p);
+  }
+  ctx->plan_tables.clear();
+}
+
+// The index tables a pass kernel looks up instead of depositing bits (layout: PassArgs64::thr / blk).
+int build_pass_tables(ntt64_ctx* ctx, const Plan& plan, ntt64_ctx::PlanTables* out) {
+  const int GB = plan.group_bits;
+  for (const ntt256::PassDesc& pd : plan.passes) {
+    const int T = pd.T, lowp = pd.T - pd.d;
+    const u32 t = 1u << (T - GB);
+    std::vector<u32> thr((size_t)(3 + pd.nrounds) * t);
+    for (u32 tid = 0; tid < t; ++tid) {
+      const u32 lam_first = deposit_host(tid, pd.tmap[0], T - GB);
+      const u32 lam_last = deposit_host(tid, pd.tmap[pd.nrounds - 1], T - GB);
+      thr[tid] = deposit_host(lam_first, pd.in_pos, T);
+      thr[t + tid] = deposit_host(lam_last, pd.out_pos, T);
+      u32 jl = 0;
+      for (int i = 0; i < lowp; ++i) jl += ((lam_last >> i) & 1u) * pd.wt_loc[i];
+      thr[2 * t + tid] = jl;
+      for (int r = 0; r < pd.nrounds; ++r) {
+        const u32 lam = deposit_host(tid, pd.tmap[r], T - GB);
+        thr[(size_t)(3 + r) * t + tid] = lam | (swz_host(lam) << 16);
+      }
+    }
+    const size_t nblk = (size_t)1 << pd.nblk_bits;
+    std::vector<uint2> blk(nblk);
+    for (size_t b = 0; b < nblk; ++b) {
+      u32 jl = pd.jlow_const;
+      for (int i = 0; i < pd.nblk_bits; ++i) jl += (u32)((b >> i) & 1) * pd.wt_blk[i];
+      blk[b] = make_uint2(deposit_host(b, pd.blk_pos, pd.nblk_bits), jl);
+    }
+    u32* d_thr = nullptr;
+    uint2* d_blk = nullptr;
+    CTX_CUDA(cudaMalloc((void**)&d_thr, thr.size() * 4));
+    out->thr.push_back(d_thr);
+    CTX_CUDA(cudaMalloc((void**)&d_blk, blk.size() * 8));
+    out->blk.push_back(d_blk);
+    // plain (synchronous) copies from pageable memory: complete before any kernel launched afterwards starts
+    CTX_CUDA(cudaMemcpy(d_thr, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice));
+    CTX_CUDA(cudaMemcpy(d_blk, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice));
+  }
+  CTX_CUDA(cudaDeviceSynchronize());  // the DMA of a pageable copy may trail its return; callers' streams need not be blocking
+  return NTT256_OK;
+}
+
+int get_plan(ntt64_ctx* ctx, int log_n, int batch, const Plan** out, const ntt64_ctx::PlanTables** tabs) {
+  PlanKey64 key;
+  key.log_n = log_n;
+  choose_shape(ctx, log_n, batch, &key.tile_bits, &key.group_bits, &key.coalesce);
+  auto it = ctx->plans.find(key);
+  if (it == ctx->plans.end()) {
+    Plan plan;
+    if (!plan_for(log_n, key.tile_bits, key.group_bits, key.coalesce, ctx->max_log_n, &plan)) return NTT256_ERR_PLAN;
+    ntt64_ctx::PlanTables pt;
+    int rc = build_pass_tables(ctx, plan, &pt);
+    if (rc) {
+      for (u32* p : pt.thr) cudaFree(p);
+      for (uint2* p : pt.blk) cudaFree(p);
+      return rc;
+    }
+    ctx->plan_tables.emplace(key, pt);
+    it = ctx->plans.emplace(key, plan).first;
+  }
+  *out = &it->second;
+  *tabs = &ctx->plan_tables.find(key)->second;
+  return NTT256_OK;
+}
+
+template <bool GL>
+void launch_pass(int gb, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const u64* in, u64* out,
+                 const PassArgs64& A) {
+  if (gb == 4 && threads <= 256) ntt64_pass16d_kernel<GL><<<grid, threads, smem, stream>>>(in, out, A);
+  else if (gb == 4) ntt64_pass16_kernel<GL><<<grid, threads, smem, stream>>>(in, out, A);
+  else ntt64_pass4_kernel<GL><<<grid, threads, smem, stream>>>(in, out, A);
+}
+
+template <bool GL>
+bool set_smem_limits() {
+  const int big = 8 << kMaxTile64, small = 8 << 12;
+  return cudaFuncSetAttribute(ntt64_pass16_kernel<GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess &&
+         cudaFuncSetAttribute(ntt64_pass16d_kernel<GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, small) == cudaSuccess &&
+         cudaFuncSetAttribute(ntt64_pass4_kernel<GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, small) == cudaSuccess;
+}
+
+struct Fuse64 {
+  const u64* in_scale = nullptr;
+  const u64* out_scale = nullptr;
+  bool out_has_ninv = false;  // out_scale already carries 1/n
+};
+
+int transform(ntt64_ctx* ctx, void* d_data, int log_n, int batch, bool inverse, cudaStream_t stream,
+              const Fuse64* fuse = nullptr) {
+  if (!ctx || !d_data || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  const bool scale = inverse && !(fuse && fuse->out_has_ninv);
+  const u64 ninv_tab = ctx->hf.tab(ctx->hf.inv((1ull << log_n) % ctx->hf.p));
+  if (log_n < 3) {
+    // the end-pass companions of such sizes are applied by their callers (coset_*), never here
+    if (log_n == 0) {
+      return NTT256_OK;
+    }
+    TinyArgs64 A;
+    std::memset(&A, 0, sizeof(A));
+    A.f = ctx->fp;
+    A.log_n = log_n;
+    A.w4 = ctx->w4[inverse ? 1 : 0];
+    A.do_scale = scale ? 1 : 0;
+    A.scale = ninv_tab;
+    A.batch = (unsigned long long)batch;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((A.batch + threads - 1) / threads);
+    if (ctx->hf.gl) ntt64_tiny_kernel<true><<<blocks, threads, 0, stream>>>((u64*)d_data, A);
+    else ntt64_tiny_kernel<false><<<blocks, threads, 0, stream>>>((u64*)d_data, A);
+    ++ctx->launches;
+    CTX_CUDA(cudaGetLastError());
+    return NTT256_OK;
+  }
+  const Plan* plan = nullptr;
+  const ntt64_ctx::PlanTables* tabs = nullptr;
+  int rc = get_plan(ctx, log_n, batch, &plan, &tabs);
+  if (rc) return rc;
+  PassArgs64 A;
+  std::memset(&A, 0, sizeof(A));
+  A.f = ctx->fp;
+  A.om_hi = ctx->om_hi;
+  A.om_lo = ctx->om_lo;
+  A.loc = ctx->loc;
+  A.hi_bits = ctx->hi_bits;
+  A.lo_bits = ctx->lo_bits;
+  A.loc_bits = ctx->loc_bits;
+  A.inverse = inverse ? 1 : 0;
+  std::memcpy(A.c16, ctx->c16[inverse ? 1 : 0], sizeof(A.c16));
+  A.batch_stride = 1ull << log_n;
+  A.scaled_round = -1;
+  A.scale = ninv_tab;
+  const u64* loc_scaled = nullptr;
+  if (scale && plan->passes.back().nrounds >= 2) {
+    // 1/n rides on the round twiddles of the last pass's first round (all sixteen elements of that round are
+    // multiplied, the one whose twiddle is 1 by 1/n itself)
+    auto it = ctx->loc_scaled.find(log_n);
+    if (it == ctx->loc_scaled.end()) {
+      u64* tab = nullptr;
+      const unsigned long long count = 1ull << ctx->loc_bits;
+      CTX_CUDA(cudaMalloc((void**)&tab, count * 8));
+      if (ctx->hf.gl) table_scale_kernel64<true><<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(tab, ctx->loc, count, ctx->fp, ninv_tab);
+      else table_scale_kernel64<false><<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(tab, ctx->loc, count, ctx->fp, ninv_tab);
+      ++ctx->launches;
+      CTX_CUDA(cudaGetLastError());
+      CTX_CUDA(cudaStreamSynchronize(stream));  // one-off: later calls may use other streams
+      it = ctx->loc_scaled.emplace(log_n, tab).first;
+    }
+    loc_scaled = it->second;
+  }
+  const int GB = plan->group_bits;
+  const int kSlice = 65535;
+  for (int b0 = 0; b0 < batch; b0 += kSlice) {
+    const int nb = std::min(kSlice, batch - b0);
+    u64* p = (u64*)d_data + ((size_t)b0 << log_n);
+    for (size_t i = 0; i < plan->passes.size(); ++i) {
+      A.pd = plan->passes[i];
+      A.scaled_round = -1;
+      A.loc_scaled = nullptr;
+      const bool last_pass = (i + 1 == plan->passes.size());
+      if (scale && last_pass) {
+        if (loc_scaled) {
+          A.scaled_round = 0;
+          A.loc_scaled = loc_scaled;
+        } else {
+          A.pd.scale_out = 1;
+        }
+      }
+      A.thr = tabs->thr[i];
+      A.blk = tabs->blk[i];
+      A.in_scale = (fuse && i == 0) ? fuse->in_scale : nullptr;
+      A.out_scale = (fuse && last_pass) ? fuse->out_scale : nullptr;
+      const int T = A.pd.T;
+      const unsigned long long nblk = 1ull << A.pd.nblk_bits;
+      if (nblk > 0x7fffffffull) return NTT256_ERR_ARG;
+      dim3 grid((unsigned)nblk, (unsigned)nb, 1);
+      const unsigned threads = 1u << (T - GB);
+      const size_t smem = (size_t)8 << T;
+      if (ctx->hf.gl) launch_pass<true>(GB, grid, threads, smem, stream, p, p, A);
+      else launch_pass<false>(GB, grid, threads, smem, stream, p, p, A);
+      ++ctx->launches;
+      CTX_CUDA(cudaGetLastError());
+    }
+  }
+  return NTT256_OK;
+}
+
+int ensure_stage(ntt64_ctx* ctx, size_t bytes) {
+  if (bytes > ctx->stage_bytes) {
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr;
+    ctx->stage_bytes = 0;
+    CTX_CUDA(cudaMalloc(&ctx->d_stage, bytes));
+    ctx->stage_bytes = bytes;
+  }
+  return NTT256_OK;
+}
+
+// Host buffers in, host buffers out.  One transform (or a small call): H2D, passes, D2H on the default stream.
+// A batch: chunks of ~32 MiB through a three-slot ring on three streams, so uplink, kernels and downlink work on
+// different chunks at the same time.
+int transform_host(ntt64_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch, bool inverse) {
+  if (!ctx || !h_in || !h_out || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  const size_t one = ((size_t)1 << log_n) * 8;
+  const size_t bytes = one * batch;
+  const size_t kChunkBytes = (size_t)32 << 20;
+  const int per_chunk = (int)std::max<size_t>(1, kChunkBytes / one);
+  if (batch < 2 * per_chunk || batch < 4) {
+    int rc = ensure_stage(ctx, bytes);
+    if (rc) return rc;
+    CTX_CUDA(cudaMemcpyAsync(ctx->d_stage, h_in, bytes, cudaMemcpyHostToDevice, 0));
+    rc = transform(ctx, ctx->d_stage, log_n, batch, inverse, 0);
+    if (rc) return rc;
+    CTX_CUDA(cudaMemcpyAsync(h_out, ctx->d_stage, bytes, cudaMemcpyDeviceToHost, 0));
+    CTX_CUDA(cudaStreamSynchronize(0));
+    return NTT256_OK;
+  }
+  if (!ctx->s_h2d) {
+    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) {
+      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t slot_bytes = one * per_chunk;
+  int rc = ensure_stage(ctx, 3 * slot_bytes);
+  if (rc) return rc;
+  const int nchunks = (batch + per_chunk - 1) / per_chunk;
+  for (int c = 0; c < nchunks; ++c) {
+    const int slot = c % 3;
+    const int b0 = c * per_chunk, nb = std::min(per_chunk, batch - b0);
+    char* d = (char*)ctx->d_stage + slot * slot_bytes;
+    if (c >= 3) CTX_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_out[slot], 0));  // slot drained
+    CTX_CUDA(cudaMemcpyAsync(d, (const char*)h_in + (size_t)b0 * one, (size_t)nb * one, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CTX_CUDA(cudaEventRecord(ctx->ev_in[slot], ctx->s_h2d));
+    CTX_CUDA(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_in[slot], 0));
+    rc = transform(ctx, d, log_n, nb, inverse, ctx->s_comp);
+    if (rc) return rc;
+    CTX_CUDA(cudaEventRecord(ctx->ev_done[slot], ctx->s_comp));
+    CTX_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[slot], 0));
+    CTX_CUDA(cudaMemcpyAsync((char*)h_out + (size_t)b0 * one, d, (size_t)nb * one, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CTX_CUDA(cudaEventRecord(ctx->ev_out[slot], ctx->s_d2h));
+  }
+  CTX_CUDA(cudaStreamSynchronize(ctx->s_d2h));
+  CTX_CUDA(cudaStreamSynchronize(ctx->s_comp));
+  return NTT256_OK;
+}
+
+void free_coset(ntt64_ctx::Coset& c) {
+  if (c.direct) cudaFree(c.direct);
+  if (c.hi) cudaFree(c.hi);
+  if (c.lo) cudaFree(c.lo);
+}
+
+// shift^j tables (optionally times 1/n), cached per (shift, log_n, with_ninv); at most four are kept
+int get_coset(ntt64_ctx* ctx, u64 shift, int log_n, bool with_ninv, const ntt64_ctx::Coset** out, cudaStream_t stream) {
+  for (auto& c : ctx->cosets)
+    if (c.shift == shift && c.log_n == log_n && c.with_ninv == (with_ninv ? 1 : 0)) {
+      *out = &c;
+      return NTT256_OK;
+    }
+  if (ctx->cosets.size() >= 4) {
+    cudaDeviceSynchronize();
+    free_coset(ctx->cosets.front());
+    ctx->cosets.erase(ctx->cosets.begin());
+  }
+  ntt64_ctx::Coset c;
+  std::memset(&c, 0, sizeof(c));
+  c.shift = shift;
+  c.log_n = log_n;
+  c.with_ninv = with_ninv ? 1 : 0;
+  const u64 start = with_ninv ? ctx->hf.inv((1ull << log_n) % ctx->hf.p) : 1;
+  int rc;
+  if (((size_t)8 << log_n) <= kCosetDirectMax64) {
+    rc = build_power_table(ctx, &c.direct, shift, log_n, start, stream);
+    if (rc) return rc;
+  } else {
+    c.lo_bits = log_n / 2;
+    rc = build_power_table(ctx, &c.lo, shift, c.lo_bits, start, stream);
+    if (rc) return rc;
+    rc = build_power_table(ctx, &c.hi, pow2k(ctx->hf, shift, c.lo_bits), log_n - c.lo_bits, 1, stream);
+    if (rc) {
+      cudaFree(c.lo);
+      return rc;
+    }
+  }
+  ctx->cosets.push_back(c);
+  *out = &ctx->cosets.back();
+  return NTT256_OK;
+}
+
+int coset_scale(ntt64_ctx* ctx, void* d_data, int log_n, int batch, const ntt64_ctx::Coset& c, cudaStream_t stream) {
+  const unsigned long long total = (unsigned long long)batch << log_n;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  const u64* hi = c.direct ? c.direct : c.hi;
+  // a direct table is its own "hi" table with no low part: lo_bits = 0 and lo[0] = 1 is what om_lo[0] holds
+  const u64* lo = c.direct ? ctx->om_lo : c.lo;
+  const int lo_bits = c.direct ? 0 : c.lo_bits;
+  if (ctx->hf.gl) coset_scale_kernel64<true><<<blocks, threads, 0, stream>>>((u64*)d_data, total, log_n, lo_bits, hi, lo, ctx->fp);
+  else coset_scale_kernel64<false><<<blocks, threads, 0, stream>>>((u64*)d_data, total, log_n, lo_bits, hi, lo, ctx->fp);
+  ++ctx->launches;
+  CTX_CUDA(cudaGetLastError());
+  return NTT256_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ntt64_ctx_create(ntt64_ctx** out, int device, uint64_t p, uint64_t g, int max_log_n) {
+  if (!out || max_log_n < 1 || max_log_n > 32) return NTT256_ERR_ARG;
+  *out = nullptr;
+  if (!(p & 1) || p < 3) return NTT256_ERR_FIELD;
+  if (p != kGoldilocksP && (p >> 63)) return NTT256_ERR_FIELD;  // the Montgomery instance needs p < 2^63
+  if (g == 0 || g >= p) return NTT256_ERR_FIELD;
+  if (max_log_n < 64 && ((p - 1) & ((1ull << max_log_n) - 1ull))) return NTT256_ERR_FIELD;
+  ntt64_ctx* ctx = new (std::nothrow) ntt64_ctx();
+  if (!ctx) return NTT256_ERR_NOMEM;
+  ctx->device = device;
+  ctx->max_log_n = max_log_n;
+  ctx->hf.init(p);
+  ctx->fp.p = p;
+  ctx->fp.np = ctx->hf.np;
+  const HostField64& hf = ctx->hf;
+  // w_N = g^((p-1)/N) must have exact order N
+  ctx->wN = hf.pow(g, (p - 1) >> max_log_n);
+  ctx->wN_inv = hf.inv(ctx->wN);
+  if (pow2k(hf, ctx->wN, max_log_n - 1) != p - 1) {
+    delete ctx;
+    return NTT256_ERR_FIELD;
+  }
+  ctx->hi_bits = std::min(max_log_n, kHiBits64);
+  ctx->lo_bits = max_log_n - ctx->hi_bits;
+  ctx->loc_bits = std::min(max_log_n, kLocBits64);
+  std::memset(ctx->c16, 0, sizeof(ctx->c16));
+  // constants of the register rounds: powers of w_16 (of w_2^max_log_n when the context is smaller: only the
+  // powers that exist are ever indexed, scaled accordingly)
+  for (int dir = 0; dir < 2; ++dir) {
+    const u64 w = dir ? ctx->wN_inv : ctx->wN;
+    if (max_log_n >= 4) {
+      const u64 w16 = pow2k(hf, w, max_log_n - 4);
+      u64 a = w16;
+      for (int k = 0; k < 7; ++k) {
+        ctx->c16[dir][k] = hf.tab(a);
+        a = hf.mul(a, w16);
+      }
+    } else {
+      // w_16^e with e a multiple of 16 / 2^max_log_n
+      const int step = 16 >> max_log_n;
+      u64 a = w;
+      for (int e = step; e <= 7; e += step) {
+        ctx->c16[dir][e - 1] = hf.tab(a);
+        a = hf.mul(a, w);
+      }
+    }
+    ctx->w4[dir] = max_log_n >= 2 ? hf.tab(pow2k(hf, w, max_log_n - 2)) : 0;
+  }
+  auto fail = [&](int code) {
+    ntt64_ctx_destroy(ctx);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTT256_ERR_CUDA);
+  if (!(hf.gl ? set_smem_limits<true>() : set_smem_limits<false>())) return fail(NTT256_ERR_CUDA);
+  int rc = build_power_table(ctx, &ctx->om_hi, pow2k(hf, ctx->wN, ctx->lo_bits), ctx->hi_bits);
+  if (rc) return fail(rc);
+  rc = build_power_table(ctx, &ctx->om_lo, ctx->wN, ctx->lo_bits);
+  if (rc) return fail(rc);
+  rc = build_power_table(ctx, &ctx->loc, pow2k(hf, ctx->wN, max_log_n - ctx->loc_bits), ctx->loc_bits);
+  if (rc) return fail(rc);
+  *out = ctx;
+  return NTT256_OK;
+}
+
+void ntt64_ctx_destroy(ntt64_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->om_hi) cudaFree(ctx->om_hi);
+  if (ctx->om_lo) cudaFree(ctx->om_lo);
+  if (ctx->loc) cudaFree(ctx->loc);
+  for (auto& kv : ctx->loc_scaled) cudaFree(kv.second);
+  free_plan_tables(ctx);
+  for (auto& c : ctx->cosets) free_coset(c);
+  if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+  if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+  if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+  for (int i = 0; i < 3; ++i) {
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+  }
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  delete ctx;
+}
+
+int ntt64_ctx_set_tuning(ntt64_ctx* ctx, int tile_bits, int coalesce_bits) {
+  if (!ctx || tile_bits < 3 || tile_bits > kMaxTile64 || coalesce_bits < 0 || coalesce_bits > 6 || coalesce_bits > tile_bits)
+    return NTT256_ERR_ARG;
+  ctx->tile_bits = tile_bits;
+  ctx->coalesce_bits = coalesce_bits;
+  ctx->auto_shape = false;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->plans.clear();  // loc_scaled tables depend on log_n only and stay valid
+  free_plan_tables(ctx);
+  return NTT256_OK;
+}
+
+int ntt64_forward(ntt64_ctx* ctx, void* d_data, int log_n, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, 1, false, (cudaStream_t)stream);
+}
+int ntt64_inverse(ntt64_ctx* ctx, void* d_data, int log_n, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, 1, true, (cudaStream_t)stream);
+}
+int ntt64_forward_batch(ntt64_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, batch, false, (cudaStream_t)stream);
+}
+int ntt64_inverse_batch(ntt64_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream) {
+  return transform(ctx, d_data, log_n, batch, true, (cudaStream_t)stream);
+}
+int ntt64_forward_host(ntt64_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch) {
+  return transform_host(ctx, h_in, h_out, log_n, batch, false);
+}
+int ntt64_inverse_host(ntt64_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch) {
+  return transform_host(ctx, h_in, h_out, log_n, batch, true);
+}
+
+int ntt64_coset_forward(ntt64_ctx* ctx, void* d_data, int log_n, int batch, uint64_t shift, ntt256_stream stream) {
+  if (!ctx || !d_data || log_n < 0 || log_n > ctx->max_log_n || batch < 1 || shift == 0 || shift >= ctx->hf.p)
+    return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  if (log_n == 0) return NTT256_OK;
+  const ntt64_ctx::Coset* c = nullptr;
+  int rc = get_coset(ctx, shift, log_n, false, &c, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (c->direct && log_n >= 3) {
+    Fuse64 fz;
+    fz.in_scale = c->direct;  // shift^j multiplies the elements as the first pass loads them
+    return transform(ctx, d_data, log_n, batch, false, (cudaStream_t)stream, &fz);
+  }
+  rc = coset_scale(ctx, d_data, log_n, batch, *c, (cudaStream_t)stream);
+  if (rc) return rc;
+  return transform(ctx, d_data, log_n, batch, false, (cudaStream_t)stream);
+}
+
+int ntt64_coset_inverse(ntt64_ctx* ctx, void* d_data, int log_n, int batch, uint64_t shift, ntt256_stream stream) {
+  if (!ctx || !d_data || log_n < 0 || log_n > ctx->max_log_n || batch < 1 || shift == 0 || shift >= ctx->hf.p)
+    return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  if (log_n == 0) return NTT256_OK;
+  const u64 sinv = ctx->hf.inv(shift);
+  const ntt64_ctx::Coset* c = nullptr;
+  int rc = get_coset(ctx, sinv, log_n, true, &c, (cudaStream_t)stream);
+  if (rc) return rc;
+  Fuse64 fz;
+  fz.out_has_ninv = true;  // the table is (1/n) * shift^-k: the transform itself does not scale
+  if (c->direct && log_n >= 3) {
+    fz.out_scale = c->direct;
+    return transform(ctx, d_data, log_n, batch, true, (cudaStream_t)stream, &fz);
+  }
+  rc = transform(ctx, d_data, log_n, batch, true, (cudaStream_t)stream, &fz);
+  if (rc) return rc;
+  return coset_scale(ctx, d_data, log_n, batch, *c, (cudaStream_t)stream);
+}
+
+int ntt64_vec_mul(ntt64_ctx* ctx, void* d_out, const void* d_a, const void* d_b, unsigned long long n, ntt256_stream stream) {
+  if (!ctx || !d_out || !d_a || !d_b) return NTT256_ERR_ARG;
+  if (n == 0) return NTT256_OK;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (ctx->hf.gl)
+    vec_mul_kernel64<true><<<blocks, threads, 0, (cudaStream_t)stream>>>((u64*)d_out, (const u64*)d_a, (const u64*)d_b, n, ctx->fp, ctx->hf.r2);
+  else
+    vec_mul_kernel64<false><<<blocks, threads, 0, (cudaStream_t)stream>>>((u64*)d_out, (const u64*)d_a, (const u64*)d_b, n, ctx->fp, ctx->hf.r2);
+  ++ctx->launches;
+  CTX_CUDA(cudaGetLastError());
+  return NTT256_OK;
+}
+
+unsigned long long ntt64_launch_count(const ntt64_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* ntt64_last_cuda_error(const ntt64_ctx* ctx) { return ctx ? ctx->last_err.c_str() : ""; }
+
+size_t ntt64_plan_describe(int log_n, int batch, int max_log_n, char* buf, size_t buf_len) {
+  ntt64_ctx tmp;  // defaults only: tile / coalescing / automatic shapes
+  int T, gb, g;
+  std::string s = "{\"error\": \"no plan\"}";
+  if (log_n >= 3 && log_n <= max_log_n && batch >= 1) {
+    choose_shape(&tmp, log_n, batch, &T, &gb, &g);
+    Plan plan;
+    if (plan_for(log_n, T, gb, g, max_log_n, &plan)) s = plan.describe();
+  }
+  if (buf && buf_len) {
+    size_t m = std::min(buf_len - 1, s.size());
+    std::memcpy(buf, s.data(), m);
+    buf[m] = 0;
+  }
+  return s.size() + 1;
+}
+
+}  // extern "C"

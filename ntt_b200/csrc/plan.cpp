@@ -179,7 +179,7 @@ struct Search {
   }
 };
 
-int rounds_of(int d) { return d == 0 ? 1 : (d + 2) / 3; }
+int rounds_of(int d, int gb) { return d == 0 ? 1 : (d + gb - 1) / gb; }
 
 // Fill the round schedule of a pass: a short first round (d mod GB stages) followed by full
 // rounds; each round owns a GB-bit group of local bits (GB = log2 of the elements a thread
@@ -252,7 +252,7 @@ bool make_plan(const PlanRequest& req, Plan* out, int max_passes) {
   Search s;
   Ctx& c = s.c;
   c.Ltot = req.total_log_n >= 0 ? req.total_log_n : req.log_n;
-  c.T = std::min(req.tile_bits, kMaxTileBits);
+  c.T = std::min(req.tile_bits, std::min(req.max_tile_bits, kMaxTileBitsAny));
   std::vector<int> start = req.start;
   if (start.empty()) {
     start.resize(req.log_n);
@@ -288,7 +288,7 @@ bool make_plan(const PlanRequest& req, Plan* out, int max_passes) {
       long rounds = 0, minrun = 99, maxd = 0;
       for (auto& pc : sol) {
         int d = (int)pc.proc_pos.size();
-        rounds += rounds_of(d);
+        rounds += rounds_of(d, req.group_bits == 4 ? 4 : 3);
         int run = 0;
         while (run < (int)pc.S.size() && pc.S[run] == run) ++run;
         minrun = std::min<long>(minrun, run);
@@ -303,7 +303,7 @@ bool make_plan(const PlanRequest& req, Plan* out, int max_passes) {
   }
   if (!found) return false;
 
-  const int GB = (req.group_bits == 2 || req.group_bits == 1) ? req.group_bits : 3;
+  const int GB = (req.group_bits == 2 || req.group_bits == 1 || req.group_bits == 4) ? req.group_bits : 3;
   out->group_bits = GB;
   out->log_n = req.log_n;
   out->tile_bits = c.T;

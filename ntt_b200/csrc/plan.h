@@ -21,7 +21,8 @@
 
 namespace ntt256 {
 
-constexpr int kMaxTileBits = 12;   // 4096 elements = 128 KiB of shared memory
+constexpr int kMaxTileBits = 12;   // 4096 elements = 128 KiB of shared memory (256-bit elements)
+constexpr int kMaxTileBitsAny = 14;  // narrower elements may ask for more (PlanRequest::max_tile_bits; arrays hold 16)
 constexpr int kMaxRounds = 12;  // T = 12 in radix-8 rounds needs 4; the two-element kernel one per stage
 constexpr int kMaxIndexBits = 40;  // log2(n * batch) the descriptors can address
 
@@ -76,7 +77,9 @@ struct PlanRequest {
   int time_hi = -1, time_lo = 0;  // process j_time_hi .. j_time_lo (default log_n-1 .. 0)
   uint32_t jlow_const = 0;
   int total_log_n = -1;     // length of the whole (possibly distributed) transform; default log_n
-  int group_bits = 3;       // 3: eight elements per thread (radix-8 rounds); 2: four (radix-4); 1: two (radix-2)
+  int group_bits = 3;       // 3: eight elements per thread (radix-8 rounds); 2: four (radix-4); 1: two (radix-2);
+                            // 4: sixteen (radix-16 rounds; the 64-bit kernels, whose elements are two registers)
+  int max_tile_bits = kMaxTileBits;  // upper limit for tile_bits (<= kMaxTileBitsAny)
 };
 
 // Returns false when no plan with <= max_passes passes exists under the constraints.

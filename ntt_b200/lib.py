@@ -39,6 +39,14 @@ EXPORTS384 = [
 ]
 
 
+# every symbol include/ntt64.h declares (the 64-bit companion API, same library)
+EXPORTS64 = [
+    "ntt64_ctx_create", "ntt64_ctx_destroy", "ntt64_ctx_set_tuning", "ntt64_forward", "ntt64_inverse", "ntt64_forward_batch",
+    "ntt64_inverse_batch", "ntt64_forward_host", "ntt64_inverse_host", "ntt64_coset_forward", "ntt64_coset_inverse",
+    "ntt64_vec_mul", "ntt64_launch_count", "ntt64_last_cuda_error", "ntt64_plan_describe",
+]
+
+
 class Ntt256Error(RuntimeError):
     def __init__(self, status: int, detail: str = ""):
         self.status = status
@@ -133,6 +141,26 @@ def lib() -> ctypes.CDLL:
         L.ntt384_last_cuda_error.restype = ctypes.c_char_p
         L.ntt384_plan_describe.argtypes = [ci, ci, ctypes.c_char_p, ctypes.c_size_t]
         L.ntt384_plan_describe.restype = ctypes.c_size_t
+        u64 = ctypes.c_uint64
+        L.ntt64_ctx_create.argtypes = [ctypes.POINTER(vp), ci, u64, u64, ci]
+        L.ntt64_ctx_destroy.argtypes = [vp]
+        L.ntt64_ctx_destroy.restype = None
+        L.ntt64_ctx_set_tuning.argtypes = [vp, ci, ci]
+        for name in ("ntt64_forward", "ntt64_inverse"):
+            getattr(L, name).argtypes = [vp, vp, ci, vp]
+        for name in ("ntt64_forward_batch", "ntt64_inverse_batch"):
+            getattr(L, name).argtypes = [vp, vp, ci, ci, vp]
+        for name in ("ntt64_forward_host", "ntt64_inverse_host"):
+            getattr(L, name).argtypes = [vp, vp, vp, ci, ci]
+        for name in ("ntt64_coset_forward", "ntt64_coset_inverse"):
+            getattr(L, name).argtypes = [vp, vp, ci, ci, u64, vp]
+        L.ntt64_vec_mul.argtypes = [vp, vp, vp, vp, ctypes.c_ulonglong, vp]
+        L.ntt64_launch_count.argtypes = [vp]
+        L.ntt64_launch_count.restype = ctypes.c_ulonglong
+        L.ntt64_last_cuda_error.argtypes = [vp]
+        L.ntt64_last_cuda_error.restype = ctypes.c_char_p
+        L.ntt64_plan_describe.argtypes = [ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]
+        L.ntt64_plan_describe.restype = ctypes.c_size_t
         _LIB = L
     return _LIB
 

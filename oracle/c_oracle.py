@@ -16,7 +16,10 @@ _REF = None
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so (and oracle/_ref when /root/reference exists)."""
-    if force or not os.path.exists(os.path.join(_HERE, "liboracle.so")):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("ntt_oracle.c", "ntt_oracle_n.c", "ntt_oracle64.c")]
+    stale = os.path.exists(so) and any(os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(so) for f in srcs)
+    if force or stale or not os.path.exists(so):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/src") and (
         force or not os.path.exists(os.path.join(_HERE, "_ref", "libref_i64.so"))
@@ -109,6 +112,32 @@ def ntt384(data: np.ndarray, p: int, g: int, inverse: bool = False, threads: int
     rc = L.oracle_ntt384(_p(out), log_n, _p(pl), _p(gl), int(inverse), threads)
     if rc:
         raise ValueError(f"oracle_ntt384 rc={rc}")
+    return out
+
+
+def ntt64(data: np.ndarray, p: int, g: int, inverse: bool = False, threads: int = 1) -> np.ndarray:
+    """Out-of-place wrapper around oracle_ntt64 (ntt_oracle64.c) on a uint64 array of 2^log_n elements."""
+    L = lib()
+    out = np.array(data, dtype=np.uint64, copy=True).reshape(-1)
+    log_n = int(out.size).bit_length() - 1
+    assert out.size == 1 << log_n
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    L.oracle_ntt64.argtypes = [u64p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
+    L.oracle_ntt64.restype = ctypes.c_int
+    rc = L.oracle_ntt64(out.ctypes.data_as(u64p), log_n, p, g, int(inverse), threads)
+    if rc:
+        raise ValueError(f"oracle_ntt64 rc={rc}")
+    return out
+
+
+def splitmix64_elements(n: int, p: int, seed: int) -> np.ndarray:
+    """n seeded canonical residues below p (64-bit fields)."""
+    L = lib()
+    out = np.empty(n, dtype=np.uint64)
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    L.oracle_splitmix64_elements.argtypes = [u64p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]
+    L.oracle_splitmix64_elements.restype = None
+    L.oracle_splitmix64_elements(out.ctypes.data_as(u64p), n, p, seed)
     return out
 
 

@@ -80,14 +80,15 @@ def run_pass(data: list[int], pd: dict, p: int, w_max: int, max_log_n: int, inve
                 # what the kernel's tail_mul says: every element with a processed bit set meets a product next
                 tail_mul = (not last) or bool(pd["has_tw"]) or (scale is not None and bool(pd.get("scale_out")))
 
-                w8 = lambda k: root(k * (N // 8))
+                MB = max(3, GB)  # constant twiddles are powers of w_8 (w_16 in the sixteen-element 64-bit kernels)
+                w8 = lambda k: root(k * N // (1 << MB))
                 for k in range(nb):  # DIF stages on the top nb bits of the group, top bit first
                     bit = GB - 1 - k
                     for u in range(NE):
                         if u & (1 << bit):
                             continue
                         t = (u >> (GB - nb)) & ((1 << (nb - 1 - k)) - 1)
-                        e8 = t << (3 - (nb - k))
+                        e8 = t << (MB - (nb - k))
                         bfly(u, u | (1 << bit), e8 != 0 or (k == nb - 1 and tail_mul))
                         if e8:
                             x[u | (1 << bit)] = A.mul(x[u | (1 << bit)], w8(e8))

@@ -59,6 +59,39 @@ def test_argument_and_field_validation_384(built):
     assert L.ntt384_forward(None, None, 3, None) == ERR_ARG
 
 
+def test_exports_match_header_64(built):
+    from ntt_b200.lib import EXPORTS64
+
+    with open(os.path.join(ROOT, "include", "ntt64.h")) as f:
+        header = f.read()
+    declared = sorted(set(re.findall(r"\b(ntt64_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(EXPORTS64)
+    L = lib()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_argument_and_field_validation_64(built):
+    from ntt_b200.lib import ERR_ARG, ERR_FIELD
+
+    L = lib()
+    GL = 0xFFFFFFFF00000001
+
+    def create(p, g, max_log_n):
+        h = ctypes.c_void_p()
+        return L.ntt64_ctx_create(ctypes.byref(h), 0, p, g, max_log_n)
+
+    assert create(GL, 7, 0) == ERR_ARG
+    assert create(GL, 7, 33) == ERR_ARG                  # two-adicity of Goldilocks is 32
+    assert create(GL - 1, 7, 10) == ERR_FIELD            # even
+    assert create((1 << 63) + 1025, 3, 10) == ERR_FIELD  # the Montgomery instance needs p < 2^63
+    assert create(469762049, 3, 27) == ERR_FIELD         # 2^26 | p - 1 only
+    assert create(469762049, 4, 10) == ERR_FIELD         # a square is not a generator
+    assert create(GL, 0, 10) == ERR_FIELD
+    assert L.ntt64_forward(None, None, 3, None) == ERR_ARG
+    assert L.ntt64_vec_mul(None, None, None, None, 4, None) == ERR_ARG
+
+
 def test_strings(built):
     L = lib()
     assert L.ntt256_strerror(0) == b"ok"

@@ -78,6 +78,45 @@ def test_against_compiled_reference(built):
         assert b.tolist() == c
 
 
+def test_oracle64_reproduces_the_reference_golden_vectors(built):
+    """ntt_oracle64.c (the checker of the 64-bit GPU path) on the outputs of the reference's own NTT()
+    (p = 469762049, x[j] = j), single- and multi-threaded, and its inverse."""
+    g = _load("ref_i64_kat.json")
+    for case in g["cases"]:
+        n = 1 << case["log_n"]
+        x = np.arange(n, dtype=np.uint64)
+        for threads in (1, 4):
+            X = co.ntt64(x, g["p"], g["g"], threads=threads)
+            assert hashlib.sha256(X.astype("<i8").tobytes()).hexdigest() == case["sha256_i64le"]
+            assert X[:8].tolist() == case["head"][: min(8, n)]
+        assert np.array_equal(co.ntt64(X, g["p"], g["g"], inverse=True), x)
+
+
+def test_oracle64_against_compiled_reference_and_python(built):
+    """Random inputs: the reference's compiled NTT() (when oracle/_ref exists), the Python oracle and the C
+    64-bit oracle agree over the reference's modulus; the Python and C oracles agree over Goldilocks."""
+    rng = np.random.default_rng(64)
+    R = co.ref_lib()
+    i64p = ctypes.POINTER(ctypes.c_longlong)
+    P, G = 469762049, 3
+    for log_n in (1, 2, 5, 9, 12):
+        x = rng.integers(0, P, size=1 << log_n, dtype=np.int64)
+        c = co.ntt64(x.astype(np.uint64), P, G, threads=2)
+        assert c.tolist() == po.ntt_ref(x.tolist(), po.REF29)
+        if R is not None:
+            a = x.copy()
+            R.ref_ntt_i64(a.ctypes.data_as(i64p), log_n)
+            assert a.tolist() == c.tolist()
+    GL = po.Field("goldilocks", 0xFFFFFFFF00000001, 7)
+    for log_n in (0, 1, 3, 8, 11):
+        x = co.splitmix64_elements(1 << log_n, GL.p, 7 + log_n)
+        # extreme residues too
+        x[: min(4, x.size)] = np.array([GL.p - 1, 0, 0xFFFFFFFF, GL.p - 0xFFFFFFFF], dtype=np.uint64)[: min(4, x.size)]
+        c = co.ntt64(x, GL.p, GL.g, threads=3)
+        assert [int(v) for v in c] == po.ntt_ref([int(v) for v in x], GL)
+        assert np.array_equal(co.ntt64(c, GL.p, GL.g, inverse=True, threads=2), x)
+
+
 def test_bigfield_golden(built):
     g = _load("bigfield_kat.json")
     for case in g["cases"]:

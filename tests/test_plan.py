@@ -108,3 +108,24 @@ def test_384_bit_plans_execute_to_the_oracle(built, L):
     x = [rng.randrange(F.p) for _ in range(1 << L)]
     want = po.ntt_ref(x, F)
     assert plan_sim.run_plan(x, plan, F.p, F.g, 14) == want
+
+
+@pytest.mark.parametrize("L,batch", [(3, 1), (4, 1), (5, 1), (8, 1), (10, 1), (12, 1), (13, 1), (14, 1), (15, 1),
+                                     (16, 1), (3, 100000), (6, 10000), (9, 4096), (12, 256)])
+def test_64_bit_plans_execute_to_the_oracle(built, L, batch):
+    """The plans ntt64_forward runs for a call of `batch` transforms of 2^L points (sixteen elements per thread
+    in radix-16 rounds, or four for small calls), executed by the kernel model over the Goldilocks field and
+    over the reference's own modulus."""
+    from ntt_b200.api64 import plan_describe64
+
+    max_log_n = 16
+    plan = plan_describe64(L, batch, max_log_n)
+    assert "error" not in plan and plan["group_bits"] in (2, 4)
+    assert all(pd["T"] >= plan["group_bits"] for pd in plan["passes"])
+    _check_plan_invariants(plan, L, 14, 0)
+    rng = random.Random(L * 7 + batch)
+    for F in (po.Field("goldilocks", 0xFFFFFFFF00000001, 7), po.REF29):
+        x = [rng.randrange(F.p) for _ in range(1 << L)]
+        want = po.ntt_ref(x, F)
+        assert plan_sim.run_plan(x, plan, F.p, F.g, max_log_n) == want
+        assert plan_sim.run_plan(want, plan, F.p, F.g, max_log_n, inverse=True) == x
