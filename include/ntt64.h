@@ -39,6 +39,11 @@ void ntt64_ctx_destroy(ntt64_ctx* ctx);
  * 12), coalesce_bits in [0,6] (global access runs of >= 2^coalesce_bits elements; default 4 = 128 bytes). */
 int ntt64_ctx_set_tuning(ntt64_ctx* ctx, int tile_bits, int coalesce_bits);
 
+/* Goldilocks only: every 64th root of unity of that field is a power of two, so with the usual generator the
+ * constant twiddles inside a register round (powers of w_16) are applied by shifts instead of products.  On by
+ * default whenever w_16 allows it; enable = 0 keeps them on the multiplier (testing: same bits either way). */
+int ntt64_ctx_set_shift_twiddles(ntt64_ctx* ctx, int enable);
+
 int ntt64_forward(ntt64_ctx* ctx, void* d_data, int log_n, ntt256_stream stream);
 int ntt64_inverse(ntt64_ctx* ctx, void* d_data, int log_n, ntt256_stream stream); /* includes 1/n */
 /* `batch` contiguous transforms of 2^log_n points each (independent polynomials; shard across GPUs by

@@ -61,6 +61,10 @@ class Ntt64:
     def set_tuning(self, tile_bits: int, coalesce_bits: int):
         self._check(self._L.ntt64_ctx_set_tuning(self._h, tile_bits, coalesce_bits))
 
+    def set_shift_twiddles(self, enable: bool):
+        """Goldilocks: constant twiddles of the register rounds by shifts (default) or on the multiplier."""
+        self._check(self._L.ntt64_ctx_set_shift_twiddles(self._h, int(bool(enable))))
+
     @staticmethod
     def _ptr(data, n_elements: int) -> int:
         if data.numel() * data.element_size() != n_elements * 8 or not data.is_cuda or not data.is_contiguous():

@@ -81,9 +81,11 @@ struct ntt64_ctx {
   u64 *om_hi = nullptr, *om_lo = nullptr, *loc = nullptr;
   int hi_bits = 0, lo_bits = 0, loc_bits = 0;
   u64 c16[2][7];  // table format
+  int k16[2] = {0, 0};  // Goldilocks: w_16^(+-1) = 2^(12 k16) when k16 is one of the compiled-in values (13, 3), else 0
   u64 w4[2];
   int tile_bits = kTileBits64, coalesce_bits = kCoalesce64;
   bool auto_shape = true;
+  bool use_shift_twiddles = true;  // testing knob: false keeps the constant twiddles on the multiplier
   struct PlanTables {  // per pass: the index tables of PassArgs64 (one device allocation each)
     std::vector<u32*> thr;
     std::vector<uint2*> blk;
@@ -286,20 +288,32 @@ int get_plan(ntt64_ctx* ctx, int log_n, int batch, const Plan** out, const ntt64
   return NTT256_OK;
 }
 
-template <bool GL>
-void launch_pass(int gb, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const u64* in, u64* out,
-                 const PassArgs64& A) {
-  if (gb == 4 && threads <= 256) ntt64_pass16d_kernel<GL><<<grid, threads, smem, stream>>>(in, out, A);
-  else if (gb == 4) ntt64_pass16_kernel<GL><<<grid, threads, smem, stream>>>(in, out, A);
-  else ntt64_pass4_kernel<GL><<<grid, threads, smem, stream>>>(in, out, A);
+template <bool GL, int K16>
+void launch_pass_k(int gb, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const u64* in, u64* out,
+                   const PassArgs64& A) {
+  if (gb == 4 && threads <= 256) ntt64_pass16d_kernel<GL, K16><<<grid, threads, smem, stream>>>(in, out, A);
+  else if (gb == 4) ntt64_pass16_kernel<GL, K16><<<grid, threads, smem, stream>>>(in, out, A);
+  else ntt64_pass4_kernel<GL, K16><<<grid, threads, smem, stream>>>(in, out, A);
+}
+// k16: 13 / 3 select the Goldilocks instances whose constant twiddles are shifts (w_16 = 2^(12 k16)); 0 = products
+void launch_pass(bool gl, int k16, int gb, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const u64* in,
+                 u64* out, const PassArgs64& A) {
+  if (!gl) launch_pass_k<false, 0>(gb, grid, threads, smem, stream, in, out, A);
+  else if (k16 == 13) launch_pass_k<true, 13>(gb, grid, threads, smem, stream, in, out, A);
+  else if (k16 == 3) launch_pass_k<true, 3>(gb, grid, threads, smem, stream, in, out, A);
+  else launch_pass_k<true, 0>(gb, grid, threads, smem, stream, in, out, A);
 }
 
-template <bool GL>
-bool set_smem_limits() {
+template <bool GL, int K16>
+bool set_smem_limits_k() {
   const int big = 8 << kMaxTile64, small = 8 << 12;
-  return cudaFuncSetAttribute(ntt64_pass16_kernel<GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess &&
-         cudaFuncSetAttribute(ntt64_pass16d_kernel<GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, small) == cudaSuccess &&
-         cudaFuncSetAttribute(ntt64_pass4_kernel<GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, small) == cudaSuccess;
+  return cudaFuncSetAttribute(ntt64_pass16_kernel<GL, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess &&
+         cudaFuncSetAttribute(ntt64_pass16d_kernel<GL, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, small) == cudaSuccess &&
+         cudaFuncSetAttribute(ntt64_pass4_kernel<GL, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, small) == cudaSuccess;
+}
+bool set_smem_limits(bool gl) {
+  if (!gl) return set_smem_limits_k<false, 0>();
+  return set_smem_limits_k<true, 0>() && set_smem_limits_k<true, 13>() && set_smem_limits_k<true, 3>();
 }
 
 struct Fuse64 {
@@ -399,8 +413,7 @@ int transform(ntt64_ctx* ctx, void* d_data, int log_n, int batch, bool inverse, 
       dim3 grid((unsigned)nblk, (unsigned)nb, 1);
       const unsigned threads = 1u << (T - GB);
       const size_t smem = (size_t)8 << T;
-      if (ctx->hf.gl) launch_pass<true>(GB, grid, threads, smem, stream, p, p, A);
-      else launch_pass<false>(GB, grid, threads, smem, stream, p, p, A);
+      launch_pass(ctx->hf.gl, ctx->use_shift_twiddles ? ctx->k16[inverse ? 1 : 0] : 0, GB, grid, threads, smem, stream, p, p, A);
       ++ctx->launches;
       CTX_CUDA(cudaGetLastError());
     }
@@ -582,13 +595,19 @@ int ntt64_ctx_create(ntt64_ctx** out, int device, uint64_t p, uint64_t g, int ma
       }
     }
     ctx->w4[dir] = max_log_n >= 2 ? hf.tab(pow2k(hf, w, max_log_n - 2)) : 0;
+    // Goldilocks: is w_16 = 2^(12 k) for one of the k the kernels are compiled for?
+    if (hf.gl && max_log_n >= 4) {
+      const u64 w16 = pow2k(hf, w, max_log_n - 4);
+      for (int k : {13, 3})
+        if (hf.pow(2, (u64)(12 * k)) == w16) ctx->k16[dir] = k;
+    }
   }
   auto fail = [&](int code) {
     ntt64_ctx_destroy(ctx);
     return code;
   };
   if (cudaSetDevice(device) != cudaSuccess) return fail(NTT256_ERR_CUDA);
-  if (!(hf.gl ? set_smem_limits<true>() : set_smem_limits<false>())) return fail(NTT256_ERR_CUDA);
+  if (!set_smem_limits(hf.gl)) return fail(NTT256_ERR_CUDA);
   int rc = build_power_table(ctx, &ctx->om_hi, pow2k(hf, ctx->wN, ctx->lo_bits), ctx->hi_bits);
   if (rc) return fail(rc);
   rc = build_power_table(ctx, &ctx->om_lo, ctx->wN, ctx->lo_bits);
@@ -630,6 +649,12 @@ int ntt64_ctx_set_tuning(ntt64_ctx* ctx, int tile_bits, int coalesce_bits) {
   cudaDeviceSynchronize();
   ctx->plans.clear();  // loc_scaled tables depend on log_n only and stay valid
   free_plan_tables(ctx);
+  return NTT256_OK;
+}
+
+int ntt64_ctx_set_shift_twiddles(ntt64_ctx* ctx, int enable) {
+  if (!ctx) return NTT256_ERR_ARG;
+  ctx->use_shift_twiddles = enable != 0;
   return NTT256_OK;
 }
 

@@ -50,7 +50,8 @@ struct PassArgs64 {
   const uint2* blk;
 };
 
-template <bool GL, int GB, int NB>
+// K16 != 0 (Goldilocks only): w_16 = 2^(12 K16), the constant twiddles are shifts (field64.cuh gl_sub_mul_w16)
+template <bool GL, int K16, int GB, int NB>
 NTT_DEV void round_compute64(u64* x, const PassArgs64& A, bool last, bool scaled, u32 lam0, int sb, int lowp) {
   using F = F64<GL>;
   const Params64& f = A.f;
@@ -63,10 +64,15 @@ NTT_DEV void round_compute64(u64* x, const PassArgs64& A, bool last, bool scaled
       const int v = u | (1 << bit);
       const u64 a = x[u], b = x[v];
       x[u] = F::add(a, b, f);
-      u64 dd = F::sub(a, b, f);
       const int t = (u >> (GB - NB)) & ((1 << (NB - 1 - k)) - 1);  // lower processed bits of u
       const int e16 = t << (4 - (NB - k));                         // constant twiddle as a power of w_16
-      if (e16) dd = F::mul(A.c16[e16 - 1], dd, f);
+      u64 dd;
+      if constexpr (GL && K16 != 0) {
+        dd = e16 ? gl_sub_mul_w16<K16>(a, b, e16) : F::sub(a, b, f);
+      } else {
+        dd = F::sub(a, b, f);
+        if (e16) dd = F::mul(A.c16[e16 - 1], dd, f);
+      }
       x[v] = dd;
     }
   }
@@ -95,7 +101,7 @@ NTT_DEV void round_compute64(u64* x, const PassArgs64& A, bool last, bool scaled
   }
 }
 
-template <bool GL, int GB>
+template <bool GL, int K16, int GB>
 NTT_DEV void ntt_pass_body64(const u64* data_in, u64* data_out, const PassArgs64& A, u32* smem) {
   using F = F64<GL>;
   constexpr int NE = 1 << GB;
@@ -156,13 +162,13 @@ NTT_DEV void ntt_pass_body64(const u64* data_in, u64* data_out, const PassArgs64
     {
       const bool scaled = (r == A.scaled_round);
       if (nb == 4) {
-        if constexpr (GB >= 4) round_compute64<GL, GB, 4>(x, A, last, scaled, lam0, sb, lowp);
+        if constexpr (GB >= 4) round_compute64<GL, K16, GB, 4>(x, A, last, scaled, lam0, sb, lowp);
       } else if (nb == 3) {
-        if constexpr (GB >= 3) round_compute64<GL, GB, 3>(x, A, last, scaled, lam0, sb, lowp);
+        if constexpr (GB >= 3) round_compute64<GL, K16, GB, 3>(x, A, last, scaled, lam0, sb, lowp);
       } else if (nb == 2) {
-        if constexpr (GB >= 2) round_compute64<GL, GB, 2>(x, A, last, scaled, lam0, sb, lowp);
+        if constexpr (GB >= 2) round_compute64<GL, K16, GB, 2>(x, A, last, scaled, lam0, sb, lowp);
       } else if (nb == 1) {
-        round_compute64<GL, GB, 1>(x, A, last, scaled, lam0, sb, lowp);
+        round_compute64<GL, K16, GB, 1>(x, A, last, scaled, lam0, sb, lowp);
       }
     }
 
@@ -231,25 +237,25 @@ NTT_DEV void ntt_pass_body64(const u64* data_in, u64* data_out, const PassArgs64
 }
 
 // Sixteen elements per thread: the throughput shape (tiles of up to 2^14 elements, <= 1024 threads).
-template <bool GL>
+template <bool GL, int K16>
 __global__ void __launch_bounds__(1024, 1)
 ntt64_pass16_kernel(const u64* data_in, u64* data_out, const __grid_constant__ PassArgs64 A) {
   extern __shared__ u32 smem[];
-  ntt_pass_body64<GL, 4>(data_in, data_out, A, smem);
+  ntt_pass_body64<GL, K16, 4>(data_in, data_out, A, smem);
 }
 // The same with 256 threads at most (tiles of <= 2^12 elements), compiled for four resident CTAs per SM.
-template <bool GL>
+template <bool GL, int K16>
 __global__ void __launch_bounds__(256, 4)
 ntt64_pass16d_kernel(const u64* data_in, u64* data_out, const __grid_constant__ PassArgs64 A) {
   extern __shared__ u32 smem[];
-  ntt_pass_body64<GL, 4>(data_in, data_out, A, smem);
+  ntt_pass_body64<GL, K16, 4>(data_in, data_out, A, smem);
 }
 // Four elements per thread: small, latency-bound calls (more, shorter threads).
-template <bool GL>
+template <bool GL, int K16>
 __global__ void __launch_bounds__(1024, 1)
 ntt64_pass4_kernel(const u64* data_in, u64* data_out, const __grid_constant__ PassArgs64 A) {
   extern __shared__ u32 smem[];
-  ntt_pass_body64<GL, 2>(data_in, data_out, A, smem);
+  ntt_pass_body64<GL, K16, 2>(data_in, data_out, A, smem);
 }
 
 // out[i] = prod over set bits k of i of pw[k] (pw[k] = w^(2^k) in the field's table format), i.e. w^i;

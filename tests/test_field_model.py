@@ -309,3 +309,80 @@ def test_a_pass_started_from_the_edge_of_the_lazy_range():
         plan_sim.run_pass(b, pd, p, w_max, 16)
         assert [v % p for v in a] == b
         assert A.max_excess < (1 << 226)
+
+
+# ---------------------------------------------------------------- 64-bit fields (ntt_b200/csrc/field64.cuh)
+GL_P = 0xFFFFFFFF00000001
+M32 = 0xFFFFFFFF
+
+
+def _gl_sub(a, b):
+    """gl_sub: 64-bit subtract, then subtract EPS when it borrowed (canonical a, b)."""
+    d = (a - b) & (2**64 - 1)
+    if a < b:
+        assert d >= M32  # the correction cannot borrow again
+        d -= M32
+    return d
+
+
+def _gl_reduce96(t, x2):
+    """gl_reduce96: t + x2 * EPS for any 64-bit t, +EPS on carry, one conditional subtraction of p."""
+    r = t + x2 * M32
+    if r >> 64:
+        r = (r & (2**64 - 1)) + M32
+        assert r < 2**64  # cannot carry again
+    r0, r1 = r & M32, r >> 32
+    if r1 == M32 and r0 != 0:
+        r0, r1 = r0 - 1, 0
+    return (r1 << 32) | r0
+
+
+def _gl_reduce128(x0, x1, x2, x3):
+    t = ((x1 << 32) | x0) - x3
+    if t < 0:
+        t += 2**64 - M32
+        assert t >= 0
+    return _gl_reduce96(t, x2)
+
+
+def _gl_mul(a, b):
+    x = a * b
+    return _gl_reduce128(x & M32, (x >> 32) & M32, (x >> 64) & M32, x >> 96)
+
+
+def _gl_mul_pow2(x, S):
+    q, r = divmod(S, 32)
+    assert 0 < S < 96 and r
+    x0, x1 = x & M32, x >> 32
+    z0, z1, z2 = (x0 << r) & M32, ((x1 << r) | (x0 >> (32 - r))) & M32, x1 >> (32 - r)
+    if q == 0:
+        return _gl_reduce96((z1 << 32) | z0, z2)
+    if q == 1:
+        return _gl_reduce128(0, z0, z1, z2)
+    ze = (z0 << 32) - z0
+    assert ze < GL_P and ((z2 << 32) | z1) < GL_P
+    return _gl_sub(ze, (z2 << 32) | z1)
+
+
+def test_goldilocks_limb_model():
+    """The limb-level steps of gl_mul / gl_mul_pow2 / gl_sub, with the no-second-carry claims asserted inside, on
+    extreme and random canonical operands; and the exponents the kernels use for the constant twiddles."""
+    rng = random.Random(64)
+    edge = [0, 1, 2, M32 - 1, M32, M32 + 1, 2**32 + 1, 2**63, GL_P - 1, GL_P - 2, GL_P - M32, GL_P - M32 - 1, 0xFFFFFFFE00000001,
+            0xFFFFFFFF00000000, 0x00000000FFFFFFFF, 0xFFFFFFFEFFFFFFFF]
+    vals = edge + [rng.randrange(GL_P) for _ in range(300)]
+    for a in vals:
+        for b in edge + [rng.randrange(GL_P) for _ in range(8)]:
+            assert _gl_mul(a, b) == a * b % GL_P
+            assert _gl_sub(a, b) == (a - b) % GL_P
+            assert _gl_sub(a, GL_P - b) == (a + b) % GL_P  # gl_add
+        for S in (12, 24, 36, 48, 60, 72, 84, 4, 31, 33, 63, 65, 95):
+            assert _gl_mul_pow2(a, S) == a * pow(2, S, GL_P) % GL_P
+    # w_16 = g^((p-1)/16) for g = 7 is 2^(12*13), its inverse 2^(12*3): the K16 values the kernels are compiled for
+    w16 = pow(7, (GL_P - 1) // 16, GL_P)
+    assert w16 == pow(2, 12 * 13, GL_P) and pow(w16, GL_P - 2, GL_P) == pow(2, 12 * 3, GL_P)
+    assert pow(2, 96, GL_P) == GL_P - 1
+    for K in (13, 3):
+        for e in range(1, 8):
+            s192 = 12 * K * e % 192
+            assert s192 % 96 and (s192 % 96) % 32

@@ -138,6 +138,29 @@ def test_tile_and_coalescing_variants_agree(torch_cuda):
         ctx.close()
 
 
+def test_shift_and_multiplier_twiddles_agree(torch_cuda):
+    """Goldilocks: the constant twiddles of the register rounds by shifts (default) and on the multiplier give
+    the same bits, forward and inverse, for every round shape (sizes 2^3 .. 2^17) and a non-standard generator
+    (whose w_16 the shift kernels are not compiled for) still transforms correctly."""
+    from ntt_b200.api64 import Ntt64
+    from oracle import c_oracle as co
+
+    ctx = Ntt64("goldilocks", max_log_n=18)
+    for log_n in range(3, 18):
+        x = co.splitmix64_elements(1 << log_n, GL_P, 500 + log_n)
+        want = co.ntt64(x, GL_P, GL_G, threads=4)
+        for enable in (True, False):
+            ctx.set_shift_twiddles(enable)
+            assert np.array_equal(_run(torch_cuda, ctx.forward, x, log_n), want), (log_n, enable)
+            assert np.array_equal(_run(torch_cuda, ctx.inverse, want, log_n), x), (log_n, enable)
+    ctx.close()
+    g2 = pow(GL_G, 5, GL_P)  # another generator
+    ctx = Ntt64(p=GL_P, g=g2, max_log_n=14)
+    x = co.splitmix64_elements(1 << 13, GL_P, 5)
+    assert np.array_equal(_run(torch_cuda, ctx.forward, x, 13), co.ntt64(x, GL_P, g2))
+    ctx.close()
+
+
 def test_max_two_adicity_context(torch_cuda):
     """A context for 2^32 points (Goldilocks' full two-adicity) transforms small sizes with the same bits."""
     from ntt_b200.api64 import Ntt64
