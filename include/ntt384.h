@@ -10,8 +10,10 @@
  * pointer, n = 2^log_n elements (cgbn_mem_t<384> layout, include/cgbn/cgbn_cuda.h:51-55),
  * transformed in place, natural order in and out, X[k] = sum_j x[j] * w_n^(jk) mod p with
  * w_n = g^((p-1)/n) for the generator g given at context creation; calls are asynchronous on
- * `stream`; status codes are those of ntt256.h.  SURVEY.md par. 8f row 4, first cut: one GPU,
- * batches, inverse with 1/n, element-wise product.  No CPU fallback.
+ * `stream`; status codes are those of ntt256.h.  SURVEY.md par. 8f row 4: batches, inverse with 1/n, the
+ * element-wise product, host buffers, coset transforms / pointwise factors fused into the end passes, and the
+ * local steps of the multi-GPU four-step transform (the kernels are the 12-limb instances of the same pass
+ * body as the 256-bit ones, csrc/ntt_pass_generic.cuh).  No CPU fallback.
  */
 #ifndef NTT384_H_
 #define NTT384_H_
@@ -36,6 +38,40 @@ int ntt384_inverse(ntt384_ctx* ctx, void* d_data, int log_n, ntt256_stream strea
 /* `batch` contiguous transforms of 2^log_n points each. */
 int ntt384_forward_batch(ntt384_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream);
 int ntt384_inverse_batch(ntt384_ctx* ctx, void* d_data, int log_n, int batch, ntt256_stream stream);
+
+/* Host buffers in and out (h_in may equal h_out), synchronous.  Pinned buffers are read by the first pass and
+ * written by the last pass directly (zero-copy over PCIe); pageable ones go through staged copies. */
+int ntt384_forward_host(ntt384_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch);
+int ntt384_inverse_host(ntt384_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch);
+
+/* Coset transforms (log_n >= 3): forward = NTT of x[j] * shift^j, the factors applied as the first pass loads;
+ * inverse undoes it (shift^-k applied before the last pass stores).  shift: 12 LE limbs, 0 < shift < p.  The
+ * multiplied-out table (48 * 2^log_n bytes) is built on first use and cached (two tables). */
+int ntt384_coset_forward(ntt384_ctx* ctx, void* d_data, int log_n, int batch, const uint32_t shift[12], ntt256_stream stream);
+int ntt384_coset_inverse(ntt384_ctx* ctx, void* d_data, int log_n, int batch, const uint32_t shift[12], ntt256_stream stream);
+/* Transform followed by the element-wise product with d_mul_mont (batch * 2^log_n Montgomery-form elements,
+ * i.e. the plain product with the values they represent), fused into the last pass's stores. */
+int ntt384_forward_mul(ntt384_ctx* ctx, void* d_data, const void* d_mul_mont, int log_n, int batch, ntt256_stream stream);
+int ntt384_inverse_mul(ntt384_ctx* ctx, void* d_data, const void* d_mul_mont, int log_n, int batch, ntt256_stream stream);
+
+/* Multi-GPU four-step pieces, exactly as ntt256_fourstep_* (ntt256.h): 2^log_p ranks, n = 2^log_r rows x
+ * 2^(log_n - log_r) columns, rank = column block; step 1 (column transforms + fused twiddle), one exchange of
+ * contiguous row blocks -- NCCL all-to-all, or none at all with *_peer, whose last pass stores every element
+ * straight into the destination rank's receive buffer (peer-mapped pointers, one per rank; ntt256_ipc_*) --
+ * then step 2.  The inverse pair consumes the forward's output shards and returns its input shards.
+ * ntt384_ctx_set_peer_sync arms the rank synchronisation folded into those kernels (flag buffers as for
+ * ntt256_ctx_set_peer_sync; NULL disarms). */
+int ntt384_fourstep_step1(ntt384_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank, ntt256_stream stream);
+int ntt384_fourstep_step1_peer(ntt384_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n, int log_r,
+                               int log_p, int rank, ntt256_stream stream);
+int ntt384_fourstep_step2(ntt384_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank, ntt256_stream stream);
+int ntt384_fourstep_inverse_step1(ntt384_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                                  ntt256_stream stream);
+int ntt384_fourstep_inverse_step1_peer(ntt384_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n,
+                                       int log_r, int log_p, int rank, ntt256_stream stream);
+int ntt384_fourstep_inverse_step2(ntt384_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank,
+                                  ntt256_stream stream);
+int ntt384_ctx_set_peer_sync(ntt384_ctx* ctx, void* const* flag_bufs, int nranks, int rank, double timeout_s);
 
 /* Element-wise product of n elements; mont_form = 0: canonical data (out = a*b mod p),
  * mont_form = 1: Montgomery-form data in and out (out = a*b*2^-384 mod p).  out may alias a or b. */

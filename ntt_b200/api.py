@@ -360,6 +360,85 @@ class Ntt384:
         self._check(self._L.ntt384_inverse_batch(self._h, self._ptr(data, batch << log_n), log_n, batch, _stream_handle(stream)))
         return data
 
+    # ---- host buffers (numpy uint32 [.., 12]; synchronous)
+    def _host(self, fn, x, log_n, batch, out):
+        x = np.ascontiguousarray(x, dtype=np.uint32)
+        if x.size != (batch << log_n) * 12:
+            raise ValueError("host array must hold batch * 2^log_n elements of 12 u32 limbs")
+        if out is None:
+            out = np.empty_like(x)
+        self._check(fn(self._h, x.ctypes.data, out.ctypes.data, log_n, batch))
+        return out
+
+    def forward_host(self, x, log_n: int, batch: int = 1, out=None):
+        return self._host(self._L.ntt384_forward_host, x, log_n, batch, out)
+
+    def inverse_host(self, x, log_n: int, batch: int = 1, out=None):
+        return self._host(self._L.ntt384_inverse_host, x, log_n, batch, out)
+
+    # ---- companions fused into the end passes
+    def _shift(self, shift: int):
+        return _u32p(np.array([(int(shift) >> (32 * i)) & 0xFFFFFFFF for i in range(12)], dtype=np.uint32))
+
+    def coset_forward(self, data, log_n: int, shift: int, batch: int = 1, stream=None):
+        self._check(self._L.ntt384_coset_forward(self._h, self._ptr(data, batch << log_n), log_n, batch, self._shift(shift),
+                                                 _stream_handle(stream)))
+        return data
+
+    def coset_inverse(self, data, log_n: int, shift: int, batch: int = 1, stream=None):
+        self._check(self._L.ntt384_coset_inverse(self._h, self._ptr(data, batch << log_n), log_n, batch, self._shift(shift),
+                                                 _stream_handle(stream)))
+        return data
+
+    def forward_mul(self, data, mul_mont, log_n: int, batch: int = 1, stream=None):
+        n = batch << log_n
+        self._check(self._L.ntt384_forward_mul(self._h, self._ptr(data, n), self._ptr(mul_mont, n), log_n, batch, _stream_handle(stream)))
+        return data
+
+    def inverse_mul(self, data, mul_mont, log_n: int, batch: int = 1, stream=None):
+        n = batch << log_n
+        self._check(self._L.ntt384_inverse_mul(self._h, self._ptr(data, n), self._ptr(mul_mont, n), log_n, batch, _stream_handle(stream)))
+        return data
+
+    # ---- multi-GPU four-step pieces (same names and meaning as Ntt256's: ntt_b200.dist.FourStep drives either)
+    def set_peer_sync(self, flag_ptrs=None, rank: int = 0, timeout_s: float = 0.0):
+        if flag_ptrs is None:
+            self._check(self._L.ntt384_ctx_set_peer_sync(self._h, None, 0, 0, 0.0))
+        else:
+            arr = (ctypes.c_void_p * len(flag_ptrs))(*[int(v) for v in flag_ptrs])
+            self._check(self._L.ntt384_ctx_set_peer_sync(self._h, arr, len(flag_ptrs), rank, float(timeout_s)))
+
+    def fourstep_step1(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        ptr = self._ptr(shard, 1 << (log_n - log_p))
+        self._check(self._L.ntt384_fourstep_step1(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))
+        return shard
+
+    def fourstep_step1_peer(self, shard, peer_ptrs, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        ptr = self._ptr(shard, 1 << (log_n - log_p))
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(v) for v in peer_ptrs])
+        self._check(self._L.ntt384_fourstep_step1_peer(self._h, ptr, arr, log_n, log_r, log_p, rank, _stream_handle(stream)))
+        return shard
+
+    def fourstep_step2(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        ptr = self._ptr(shard, 1 << (log_n - log_p))
+        self._check(self._L.ntt384_fourstep_step2(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))
+        return shard
+
+    def fourstep_inverse_step1(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None, peer_ptrs=None):
+        ptr = self._ptr(shard, 1 << (log_n - log_p))
+        if peer_ptrs is None:
+            self._check(self._L.ntt384_fourstep_inverse_step1(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))
+        else:
+            arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(v) for v in peer_ptrs])
+            self._check(self._L.ntt384_fourstep_inverse_step1_peer(self._h, ptr, arr, log_n, log_r, log_p, rank,
+                                                                   _stream_handle(stream)))
+        return shard
+
+    def fourstep_inverse_step2(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        ptr = self._ptr(shard, 1 << (log_n - log_p))
+        self._check(self._L.ntt384_fourstep_inverse_step2(self._h, ptr, log_n, log_r, log_p, rank, _stream_handle(stream)))
+        return shard
+
     def vec_mul(self, a, b, out=None, mont_form: bool = False, stream=None):
         n = a.numel() * a.element_size() // 48
         out = a if out is None else out

@@ -166,7 +166,7 @@ __global__ void coset_scale_direct_kernel(uint4* __restrict__ data, unsigned lon
   if (shoup) {
     ld_global_256(w, table + 4 * j);
     ld_global_256(wq, table + 4 * j + 2);
-    mul_tw<true>(x, w, wq, f);
+    mul_tw_256<true>(x, w, wq, f);
     canonicalize_wl(x, f);
   } else {
     ld_global_256(w, table + 2 * j);

@@ -1,8 +1,7 @@
-// Pass kernel for NL x 32-bit limb fields (NL = 12: 384-bit containers), SURVEY.md par. 8f row 4.
-// Same pass / round / exchange structure as ntt_pass_body in ntt_kernels.cuh, driven by the same
-// planner (plan.h), with the field layer of field_n.cuh.  Kept to what a first wider field needs:
-// in-place passes, both twiddle table paths (one or two lookups), inverse scaling in the last pass;
-// no peer stores, no streamed twiddles.  Four elements per thread (48 data registers at NL = 12).
+// Pass kernel for NL x 32-bit limb fields (NL = 12: 384-bit containers), SURVEY.md par. 8f row 4: the N-limb
+// instance of the one pass body (ntt_pass_generic.cuh, the same code the 256-bit kernels are instances of), with
+// the field layer of field_n.cuh -- so peer stores, rank synchronisation, streamed twiddles, out-of-place ends
+// and the fused companions exist for this width too.  Four elements per thread (48 data registers at NL = 12).
 // An element is NL/4 consecutive uint4 (element-major, little-endian limbs), like cgbn_mem_t<bits>
 // (/root/reference/include/cgbn/cgbn_cuda.h:51-55) for bits = 32*NL.
 #pragma once
@@ -10,27 +9,10 @@
 
 #include "field_n.cuh"
 #include "kernel_common.cuh"
+#include "ntt_pass_generic.cuh"
 #include "plan.h"
 
 namespace ntt256 {
-
-template <int NL>
-struct PassArgsN {
-  FieldParamsN<NL> f;
-  PassDesc pd;
-  const uint4* om_hi;  // w_N^(i << lo_bits), Montgomery form
-  const uint4* om_lo;  // w_N^i, i < 2^lo_bits
-  const uint4* loc;    // w_{2^loc_bits}^i (round twiddles)
-  int hi_bits, lo_bits, loc_bits;
-  int inverse;
-  u32 c8[3][NL];  // w_8^1..3 (or inverses), Montgomery form
-  u32 scale[NL];  // 1/n, Montgomery form (pd.scale_out)
-  unsigned long long batch_stride;
-  // inverse: round `scaled_round` of this pass reads loc_scaled = (1/n) * loc and multiplies every
-  // element (also the one whose twiddle is 1), which applies the 1/n without an extra product
-  int scaled_round;
-  const uint4* loc_scaled;
-};
 
 template <int NL>
 NTT_DEV void ld_el(u32* v, const uint4* p) {
@@ -74,172 +56,42 @@ NTT_DEV void bfly_n(u32* a, u32* b, const FieldParamsN<NL>& f) {
   }
 }
 
-// NB DIF stages on the top NB bits of the GB-bit register index + the round twiddle (cf. round_compute).
-template <int NL, int GB, int NB>
-NTT_DEV void round_compute_n(u32 (*x)[NL], const PassArgsN<NL>& A, bool last, bool scaled, u32 lam0, int sb, int lowp) {
-  const FieldParamsN<NL>& f = A.f;
+// The N-limb field policy of the pass body (ntt_pass_generic.cuh): Montgomery-form twiddles, values in [0, 2p)
+// between butterflies, every correction exact.
+template <int NLIMBS>
+struct FN {
+  static constexpr int NL = NLIMBS;
+  static constexpr int TW = NLIMBS;
+  using Params = FieldParamsN<NLIMBS>;
+  using Args = PassArgsT<Params, NLIMBS, NLIMBS>;
+  static NTT_DEV void ld(u32* v, const uint4* p) { ld_el<NL>(v, p); }
+  static NTT_DEV void st(uint4* p, const u32* v) { st_el<NL>(p, v); }
+  static NTT_DEV void ld_tw(u32* w, const uint4* tab, u32 idx) { ld_table_n<NL>(w, tab, idx); }
+  static NTT_DEV void mul_tw(u32* x, const u32* w, const Params& f) { mul_by_n<NL>(x, w, f); }
+  static NTT_DEV void bfly(u32* a, u32* b, const Params& f, bool) { bfly_n<NL>(a, b, f); }
+  static NTT_DEV void canon(u32* x, const Params& f) { canonicalize_n<NL>(x, f); }
+  static NTT_DEV void canon_exact(u32* x, const Params& f) { canonicalize_n<NL>(x, f); }
+  static NTT_DEV void st_tw(uint4* tab, u32 idx, const u32* w, const Args&) { st_el<NL>(tab + (NL / 4) * (size_t)idx, w); }
+  // x <- x * v[idx] / R for a caller-supplied Montgomery-form vector (= the plain product)
+  static NTT_DEV void mul_var(u32* x, const uint4* vec, u32 idx, const Params& f) {
+    u32 v[NL], r[NL];
+    ld_table_n<NL>(v, vec, idx);
+    canonicalize_n<NL>(x, f);  // the product wants its left operand below p
+    mont_mul_n<NL>(r, x, v, f);
 #pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    const int bit = GB - 1 - k;
-#pragma unroll
-    for (int u = 0; u < (1 << GB); ++u) {
-      if (u & (1 << bit)) continue;
-      bfly_n<NL>(x[u], x[u | (1 << bit)], f);
-      const int t = (u >> (GB - NB)) & ((1 << (NB - 1 - k)) - 1);
-      const int e8 = t << (3 - (NB - k));
-      if (e8) mul_by_n<NL>(x[u | (1 << bit)], A.c8[e8 - 1], f);
-    }
+    for (int k = 0; k < NL; ++k) x[k] = r[k];
   }
-  if (last) return;
-  const int pb = sb + GB - NB;
-  const int m = sb + GB - lowp;
-  const int sh = A.loc_bits - m;
-  const u32 tl_mask = (1u << (pb - lowp)) - 1u;
-  const u32 tl0 = (lam0 >> lowp) & tl_mask;
-  const int ush = sb - lowp;
-  const uint4* loc_tab = scaled ? A.loc_scaled : A.loc;
-#pragma unroll
-  for (int u = 0; u < (1 << GB); ++u) {
-    const int uproc = u >> (GB - NB);
-    int v = 0;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) v |= ((uproc >> i) & 1) << (NB - 1 - i);
-    const u32 rest = u & ((1 << (GB - NB)) - 1);
-    if (scaled || uproc != 0) {
-      const u32 tl = (tl0 | (rest << ush)) & tl_mask;
-      u32 e = (tl * (u32)v) << sh;
-      if (A.inverse) e = (0u - e);
-      e &= (1u << A.loc_bits) - 1u;
-      u32 w[NL];
-      ld_table_n<NL>(w, loc_tab, e);
-      mul_by_n<NL>(x[u], w, f);
-    }
-  }
-}
+};
+template <int NL>
+using PassArgsN = PassArgsT<FieldParamsN<NL>, NL, NL>;
 
-template <int NL, int GB>
-NTT_DEV void ntt_pass_body_n(uint4* data, const PassArgsN<NL>& A, u32* smem) {
-  constexpr int NE = 1 << GB;
-  constexpr int Q = NL / 4;  // uint4 per element
-  const PassDesc& pd = A.pd;
-  const FieldParamsN<NL>& f = A.f;
-  const int T = pd.T;
-  const int d = pd.d;
-  const u32 tid = threadIdx.x;
-  const u32 tile_words = 1u << T;
-
-  const unsigned long long blk = blockIdx.x;
-  unsigned long long base = deposit64(blk, pd.blk_pos, pd.nblk_bits);
-  u32 jlow_blk = pd.jlow_const;
-  for (int i = 0; i < pd.nblk_bits; ++i) jlow_blk += (u32)((blk >> i) & 1ull) * pd.wt_blk[i];
-  base += (unsigned long long)blockIdx.y * A.batch_stride;
-  uint4* gbase = data + Q * base;
-
-  u32 x[NE][NL];
-  const int lowp = T - d;
-
-  for (int r = 0; r < pd.nrounds; ++r) {
-    const int sb = pd.round_sb[r];
-    const int nb = pd.round_nb[r];
-    const u32 lam0 = deposit32(tid, pd.tmap[r], T - GB);
-    const bool first = (r == 0);
-    const bool last = (r == pd.nrounds - 1);
-
-    if (first) {
-      const u32 g0 = deposit32(lam0, pd.in_pos, T);
-      u32 st[GB];
-#pragma unroll
-      for (int i = 0; i < GB; ++i) st[i] = 1u << pd.in_pos[sb + i];
-#pragma unroll
-      for (int u = 0; u < NE; ++u) {
-        u32 off = g0;
-#pragma unroll
-        for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
-        ld_el<NL>(x[u], gbase + Q * (size_t)off);
-      }
-    } else {
-      const u32 w0 = swz(lam0);
-#pragma unroll
-      for (int u = 0; u < NE; ++u) {
-        const u32 w = w0 ^ swz((u32)u << sb);
-#pragma unroll
-        for (int k = 0; k < NL; ++k) x[u][k] = smem[k * tile_words + w];
-      }
-    }
-
-    const bool scaled = (r == A.scaled_round);
-    if (nb == 2) {
-      if constexpr (GB >= 2) round_compute_n<NL, GB, 2>(x, A, last, scaled, lam0, sb, lowp);
-    } else if (nb == 1) {
-      round_compute_n<NL, GB, 1>(x, A, last, scaled, lam0, sb, lowp);
-    }
-
-    if (!last) {
-      const u32 w0 = swz(lam0);
-#pragma unroll
-      for (int u = 0; u < NE; ++u) {
-        const u32 w = w0 ^ swz((u32)u << sb);
-#pragma unroll
-        for (int k = 0; k < NL; ++k) smem[k * tile_words + w] = x[u][k];
-      }
-      __syncthreads();
-    } else {
-      const u32 g0 = deposit32(lam0, pd.out_pos, T);
-      u32 st[GB];
-#pragma unroll
-      for (int i = 0; i < GB; ++i) st[i] = 1u << pd.out_pos[sb + i];
-      if (pd.has_tw) {
-        u32 jl0 = jlow_blk;
-        for (int i = 0; i < lowp; ++i) jl0 += ((lam0 >> i) & 1u) * pd.wt_loc[i];
-        u32 gw[GB];
-#pragma unroll
-        for (int i = 0; i < GB; ++i) gw[i] = (sb + i < lowp) ? pd.wt_loc[sb + i] : 0u;
-        const u32 nmask = (A.hi_bits + A.lo_bits >= 32) ? 0xffffffffu : ((1u << (A.hi_bits + A.lo_bits)) - 1u);
-        const u32 lomask = (1u << A.lo_bits) - 1u;
-        const bool two = pd.tw_lshift < A.lo_bits;
-#pragma unroll
-        for (int u = 0; u < NE; ++u) {
-          const u32 lam = lam0 | ((u32)u << sb);
-          const u32 khi = d ? (__brev(lam >> lowp) >> (32 - d)) : 0u;
-          u32 jl = jl0;
-#pragma unroll
-          for (int i = 0; i < GB; ++i) jl += ((u >> i) & 1) ? gw[i] : 0u;
-          u32 e = (jl * khi) << pd.tw_lshift;
-          if (A.inverse) e = (0u - e);
-          e &= nmask;
-          u32 w[NL];
-          ld_table_n<NL>(w, A.om_hi, e >> A.lo_bits);
-          mul_by_n<NL>(x[u], w, f);
-          if (two) {
-            ld_table_n<NL>(w, A.om_lo, e & lomask);
-            mul_by_n<NL>(x[u], w, f);
-          }
-        }
-      }
-      if (pd.scale_out) {
-#pragma unroll
-        for (int u = 0; u < NE; ++u) mul_by_n<NL>(x[u], A.scale, f);
-      }
-      if (pd.is_final) {
-#pragma unroll
-        for (int u = 0; u < NE; ++u) canonicalize_n<NL>(x[u], f);
-      }
-      if (first) __syncthreads();  // single-round pass: all loads before any permuted store
-#pragma unroll
-      for (int u = 0; u < NE; ++u) {
-        u32 off = g0;
-#pragma unroll
-        for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
-        st_el<NL>(gbase + Q * (size_t)off, x[u]);
-      }
-    }
-  }
-}
-
+// 384-bit containers: four elements per thread (48 data registers).  FZ: the launch carries element-wise
+// companions (in_scale / out_scale / out_mul).
+template <bool FZ>
 __global__ void __launch_bounds__(512, 1)
-ntt384_pass_kernel(uint4* data, const __grid_constant__ PassArgsN<12> A) {
+ntt384_pass_kernel(const uint4* data_in, uint4* data_out, const __grid_constant__ PassArgsN<12> A) {
   extern __shared__ u32 smem[];
-  ntt_pass_body_n<12, 2>(data, A, smem);
+  ntt_pass_body<2, FN<12>, FZ>(data_in, data_out, A, smem);
 }
 
 // out[i] = prod over set bits k of i of pw[k] (pw[k] = w^(2^k), Montgomery form), i.e. w^i.

@@ -5,7 +5,10 @@
 #include <cuda_runtime.h>
 
 namespace ntt256 {
-struct PassArgs;
+struct FieldParams;
+template <class PARAMS, int NL, int TWS>
+struct PassArgsT;
+using PassArgs = PassArgsT<FieldParams, 8, 16>;
 template <bool SH, bool FZ>
 void launch_pass_inst(int group_bits, bool dense, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const uint4* in,
                       uint4* out, const PassArgs& A);

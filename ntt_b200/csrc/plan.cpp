@@ -367,6 +367,82 @@ bool make_plan(const PlanRequest& req, Plan* out, int max_passes) {
   return true;
 }
 
+// Plan request of a whole transform (kind 0) or of one local step of the four-step
+// decomposition (kinds 1 and 2, SURVEY.md par. 8e), expressed in the planner's label model.
+PlanRequest fourstep_request(const FourStepKey& key, int tile_bits, int coalesce_bits, int max_log_n) {
+  PlanRequest req;
+  req.tile_bits = tile_bits;
+  req.coalesce_bits = coalesce_bits;
+  req.max_log_n = max_log_n;
+  req.log_n = key.log_n;
+  if (key.kind == 1 || key.kind == 2) {
+    const int L = key.log_n, lr = key.log_r, lp = key.log_p, lc = L - lr;
+    const int nloc = L - lp;
+    req.total_log_n = L;
+    req.start.resize(nloc);
+    req.target.resize(nloc);
+    if (key.kind == 1) {
+      // local index = j1 * (C/P) + j2_local ; rank = top lp bits of j2
+      for (int p = 0; p < lc - lp; ++p) req.start[p] = p, req.target[p] = p;
+      for (int i = 0; i < lr; ++i) {
+        req.start[lc - lp + i] = lc + i;
+        req.target[lc - lp + i] = 64 + i;  // k1 natural above j2_local
+      }
+      req.time_hi = L - 1;
+      req.time_lo = lc;
+      req.jlow_const = (uint32_t)key.rank << (lc - lp);
+    } else {
+      // received layout [src rank][k1 local][j2 local]
+      for (int p = 0; p < lc - lp; ++p) req.start[p] = p;
+      for (int c = 0; c < lr - lp; ++c) req.start[lc - lp + c] = 64 + c;
+      for (int i = 0; i < lp; ++i) req.start[lc - lp + lr - lp + i] = lc - lp + i;
+      // output [k2 mod P][k1 local][k2 div P]: every field is transformed where it lies (the two
+      // j2 fields are bit-reversed in place), so a C-point row NTT with C <= 2^tile_bits is ONE pass.
+      // k2 bit i = k_{lr+i}; bits 0..lp-1 come from the old rank bits on top.
+      for (int i = 0; i < lc - lp; ++i) req.target[i] = 64 + lr + lp + i;
+      for (int c = 0; c < lr - lp; ++c) req.target[lc - lp + c] = 64 + c;
+      for (int i = 0; i < lp; ++i) req.target[lc - lp + lr - lp + i] = 64 + lr + i;
+      req.time_hi = lc - 1;
+      req.time_lo = 0;
+      req.jlow_const = 0;
+    }
+  }
+  if (key.kind == 3 || key.kind == 4) {
+    // Distributed INVERSE that consumes the forward's output shards and returns the forward's
+    // input shards.  Its time index is K = k1 + R*k2 (the forward's frequency index), viewed as
+    // R' x C' with C' = 2^lr columns (K2 = k1) and R' = 2^lc rows (K1 = k2): the rank is again the
+    // top lp bits of the column index.  Local input layout = [k2 mod P][k1 local][k2 div P].
+    const int L = key.log_n, lr = key.log_r, lp = key.log_p, lc = L - lr;
+    const int nloc = L - lp;
+    req.total_log_n = L;
+    req.start.assign(nloc, 0);
+    req.target.assign(nloc, 0);
+    if (key.kind == 3) {
+      for (int i = 0; i < lc - lp; ++i) req.start[i] = lr + lp + i;              // k2 div P
+      for (int i = 0; i < lr - lp; ++i) req.start[lc - lp + i] = i;              // k1 local
+      for (int i = 0; i < lp; ++i) req.start[lc - lp + lr - lp + i] = lr + i;    // k2 mod P
+      // step 1 transforms K bits L-1 .. lr -> J bits 0 .. lc-1
+      for (int i = 0; i < lc - lp; ++i) req.target[i] = 64 + i;                  // j2 local, final
+      for (int i = 0; i < lr - lp; ++i) req.target[lc - lp + i] = i;             // k1 local waits
+      for (int i = 0; i < lp; ++i) req.target[lc - lp + lr - lp + i] = 64 + lc - lp + i;  // destination rank
+      req.time_hi = L - 1;
+      req.time_lo = lr;
+      req.jlow_const = (uint32_t)key.rank << (lr - lp);
+    } else {
+      for (int i = 0; i < lc - lp; ++i) req.start[i] = 64 + i;
+      for (int i = 0; i < lr - lp; ++i) req.start[lc - lp + i] = i;
+      for (int i = 0; i < lp; ++i) req.start[lc - lp + lr - lp + i] = lr - lp + i;  // the old rank bits
+      for (int i = 0; i < lc - lp; ++i) req.target[i] = 64 + i;
+      for (int m = 0; m < lr; ++m) req.target[lc - lp + m] = 64 + lc + m;           // j1 natural
+      req.time_hi = lr - 1;
+      req.time_lo = 0;
+      req.jlow_const = 0;
+    }
+  }
+  return req;
+}
+
+
 std::string Plan::describe() const {
   std::ostringstream o;
   o << "{\"log_n\": " << log_n << ", \"tile_bits\": " << tile_bits << ", \"group_bits\": " << group_bits

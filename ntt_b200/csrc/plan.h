@@ -82,6 +82,19 @@ struct PlanRequest {
   int max_tile_bits = kMaxTileBits;  // upper limit for tile_bits (<= kMaxTileBitsAny)
 };
 
+// Which piece of work a plan is for: a whole transform (kind 0) or one local step of the four-step
+// decomposition over 2^log_p ranks (SURVEY.md par. 8e): 1 / 2 = forward step 1 / 2, 3 / 4 = inverse step 1 / 2.
+struct FourStepKey {
+  int kind, log_n, log_r, log_p, rank;
+};
+// The request (start labels, targets, time range, foreign index bits) of that piece in the planner's label model;
+// shared by every container width.
+PlanRequest fourstep_request(const FourStepKey& key, int tile_bits, int coalesce_bits, int max_log_n);
+inline bool fourstep_args_ok(int log_n, int log_r, int log_p, int rank) {
+  return log_p >= 0 && log_r >= log_p && log_n - log_r >= log_p && rank >= 0 && rank < (1 << log_p) &&
+         log_n - log_p >= 3 && log_r >= 1 && log_n - log_r >= 1;
+}
+
 // Returns false when no plan with <= max_passes passes exists under the constraints.
 bool make_plan(const PlanRequest& req, Plan* out, int max_passes = 8);
 

@@ -26,42 +26,43 @@ def _log2(v: int) -> int:
     return l
 
 
-def scatter_input(x: np.ndarray, log_n: int, world: int, log_r: int | None = None) -> list[np.ndarray]:
-    """Natural-order x [n, 8] -> per-rank input shards (column blocks of the R x C view)."""
+def scatter_input(x: np.ndarray, log_n: int, world: int, log_r: int | None = None, limbs: int = 8) -> list[np.ndarray]:
+    """Natural-order x [n, limbs] -> per-rank input shards (column blocks of the R x C view); limbs = 8 for 256-bit
+    containers, 12 for 384-bit ones."""
     log_r = default_log_r(log_n) if log_r is None else log_r
     R, C = 1 << log_r, 1 << (log_n - log_r)
-    m = x.reshape(R, C, 8)
+    m = x.reshape(R, C, limbs)
     w = C // world
-    return [np.ascontiguousarray(m[:, r * w:(r + 1) * w]).reshape(-1, 8) for r in range(world)]
+    return [np.ascontiguousarray(m[:, r * w:(r + 1) * w]).reshape(-1, limbs) for r in range(world)]
 
 
-def gather_output(shards: list[np.ndarray], log_n: int, world: int, log_r: int | None = None) -> np.ndarray:
+def gather_output(shards: list[np.ndarray], log_n: int, world: int, log_r: int | None = None, limbs: int = 8) -> np.ndarray:
     """Per-rank output shards (element [k2 mod P][k1_local][k2 div P] = X[k1 + R*k2]) -> natural-order X."""
     log_r = default_log_r(log_n) if log_r is None else log_r
     R, C = 1 << log_r, 1 << (log_n - log_r)
     P = world
     # [rank][k2_low][k1_local][k2_high] -> X index k2*R + k1 with k2 = k2_low + P*k2_high, k1 = rank*(R/P) + k1_local
-    m = np.stack([s.reshape(P, R // P, C // P, 8) for s in shards], axis=0)
+    m = np.stack([s.reshape(P, R // P, C // P, limbs) for s in shards], axis=0)
     m = m.transpose(3, 1, 0, 2, 4)  # [k2_high][k2_low][rank][k1_local]
-    return np.ascontiguousarray(m).reshape(-1, 8)
+    return np.ascontiguousarray(m).reshape(-1, limbs)
 
 
-def scatter_output_layout(X: np.ndarray, log_n: int, world: int, log_r: int | None = None) -> list[np.ndarray]:
+def scatter_output_layout(X: np.ndarray, log_n: int, world: int, log_r: int | None = None, limbs: int = 8) -> list[np.ndarray]:
     """Natural-order X -> shards in the forward's OUTPUT layout (inverse of gather_output): the input
     of FourStep.inverse()."""
     log_r = default_log_r(log_n) if log_r is None else log_r
     R, C = 1 << log_r, 1 << (log_n - log_r)
     P = world
-    m = X.reshape(C // P, P, P, R // P, 8)           # [k2_high][k2_low][rank][k1_local]
+    m = X.reshape(C // P, P, P, R // P, limbs)       # [k2_high][k2_low][rank][k1_local]
     m = m.transpose(2, 1, 3, 0, 4)                   # [rank][k2_low][k1_local][k2_high]
-    return [np.ascontiguousarray(m[r]).reshape(-1, 8) for r in range(world)]
+    return [np.ascontiguousarray(m[r]).reshape(-1, limbs) for r in range(world)]
 
 
-def gather_input_layout(shards: list[np.ndarray], log_n: int, world: int, log_r: int | None = None) -> np.ndarray:
+def gather_input_layout(shards: list[np.ndarray], log_n: int, world: int, log_r: int | None = None, limbs: int = 8) -> np.ndarray:
     """Shards in the forward's INPUT layout (column blocks) -> natural order (inverse of scatter_input)."""
     log_r = default_log_r(log_n) if log_r is None else log_r
     R, C = 1 << log_r, 1 << (log_n - log_r)
-    return np.ascontiguousarray(np.concatenate([s.reshape(R, C // world, 8) for s in shards], axis=1)).reshape(-1, 8)
+    return np.ascontiguousarray(np.concatenate([s.reshape(R, C // world, limbs) for s in shards], axis=1)).reshape(-1, limbs)
 
 
 def output_location(k: int, log_n: int, world: int, log_r: int | None = None) -> tuple[int, int]:

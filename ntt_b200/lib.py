@@ -35,7 +35,10 @@ EXPORTS = [
 # every symbol include/ntt384.h declares (the 384-bit companion API, same library)
 EXPORTS384 = [
     "ntt384_ctx_create", "ntt384_ctx_destroy", "ntt384_ctx_set_tuning", "ntt384_forward", "ntt384_inverse", "ntt384_forward_batch",
-    "ntt384_inverse_batch", "ntt384_vec_mul", "ntt384_launch_count", "ntt384_last_cuda_error", "ntt384_plan_describe",
+    "ntt384_inverse_batch", "ntt384_forward_host", "ntt384_inverse_host", "ntt384_coset_forward", "ntt384_coset_inverse",
+    "ntt384_forward_mul", "ntt384_inverse_mul", "ntt384_fourstep_step1", "ntt384_fourstep_step1_peer", "ntt384_fourstep_step2",
+    "ntt384_fourstep_inverse_step1", "ntt384_fourstep_inverse_step1_peer", "ntt384_fourstep_inverse_step2",
+    "ntt384_ctx_set_peer_sync", "ntt384_vec_mul", "ntt384_launch_count", "ntt384_last_cuda_error", "ntt384_plan_describe",
 ]
 
 
@@ -135,6 +138,18 @@ def lib() -> ctypes.CDLL:
         for name in ("ntt384_forward_batch", "ntt384_inverse_batch"):
             getattr(L, name).argtypes = [vp, vp, ci, ci, vp]
         L.ntt384_vec_mul.argtypes = [vp, vp, vp, vp, ctypes.c_ulonglong, ci, vp]
+        for name in ("ntt384_forward_host", "ntt384_inverse_host"):
+            getattr(L, name).argtypes = [vp, vp, vp, ci, ci]
+        for name in ("ntt384_coset_forward", "ntt384_coset_inverse"):
+            getattr(L, name).argtypes = [vp, vp, ci, ci, u32p, vp]
+        for name in ("ntt384_forward_mul", "ntt384_inverse_mul"):
+            getattr(L, name).argtypes = [vp, vp, vp, ci, ci, vp]
+        for name in ("ntt384_fourstep_step1", "ntt384_fourstep_step2", "ntt384_fourstep_inverse_step1",
+                     "ntt384_fourstep_inverse_step2"):
+            getattr(L, name).argtypes = [vp, vp, ci, ci, ci, ci, vp]
+        for name in ("ntt384_fourstep_step1_peer", "ntt384_fourstep_inverse_step1_peer"):
+            getattr(L, name).argtypes = [vp, vp, ctypes.POINTER(vp), ci, ci, ci, ci, vp]
+        L.ntt384_ctx_set_peer_sync.argtypes = [vp, ctypes.POINTER(vp), ci, ci, ctypes.c_double]
         L.ntt384_launch_count.argtypes = [vp]
         L.ntt384_launch_count.restype = ctypes.c_ulonglong
         L.ntt384_last_cuda_error.argtypes = [vp]

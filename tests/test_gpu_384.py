@@ -217,3 +217,108 @@ def test_full_c_oracle_2p18(env):
     gotb = _run(torch, ctx.forward, x, 15, 8)
     for b in range(8):
         assert np.array_equal(gotb[b * n:(b + 1) * n], co.ntt384(x[b * n:(b + 1) * n], p, g, threads=8)), b
+
+
+def _rand384(seed, n):
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, 1 << 32, size=(n, 12), dtype=np.uint64).astype(np.uint32)
+    x[:, 11] &= 0x00FFFFFF  # below 2^376 < p
+    return x
+
+
+@pytest.mark.parametrize("log_n,world", [(12, 1), (14, 2), (16, 8), (18, 4)])
+def test_fourstep_ranks_emulated_on_one_gpu(env, log_n, world):
+    """The 384-bit four-step pieces (same pass body as the 256-bit ones): scatter -> step 1 per rank -> the
+    all-to-all by its host definition -> step 2 per rank -> gather equals the single-transform C oracle; the
+    inverse pair takes the output shards back to the input shards."""
+    from ntt_b200 import dist as nd
+    from oracle import c_oracle as co
+
+    torch, ctx, (p, g) = env
+    log_p, log_r = world.bit_length() - 1, nd.default_log_r(log_n)
+    x = _rand384(40 + log_n, 1 << log_n)
+    want = co.ntt384(x, p, g, threads=8)
+
+    def each(fn, shards):
+        out = []
+        for r, sh in enumerate(shards):
+            d = torch.from_numpy(np.ascontiguousarray(sh).view(np.int32)).cuda().view(-1)
+            fn(d, log_n, log_r, log_p, r)
+            torch.cuda.synchronize()
+            out.append(d.cpu().numpy().view(np.uint32).reshape(-1, 12))
+        return out
+
+    ins = nd.scatter_input(x, log_n, world, log_r, limbs=12)
+    s2 = each(ctx.fourstep_step2, nd.exchange_reference(each(ctx.fourstep_step1, ins), world))
+    assert np.array_equal(nd.gather_output(s2, log_n, world, log_r, limbs=12), want)
+    back = each(ctx.fourstep_inverse_step2, nd.exchange_reference(each(ctx.fourstep_inverse_step1, s2), world))
+    for r in range(world):
+        assert np.array_equal(back[r], ins[r]), r
+
+
+@pytest.mark.parametrize("log_n,world", [(14, 2), (17, 8)])
+def test_fused_peer_store_on_one_gpu(env, log_n, world):
+    """ntt384_fourstep_step1_peer with every rank's receive buffer on this GPU: the store phase of the butterfly
+    kernel delivers exactly what step 1 + all-to-all delivers."""
+    from ntt_b200 import dist as nd
+    from oracle import c_oracle as co
+
+    torch, ctx, (p, g) = env
+    lp, lr = world.bit_length() - 1, nd.default_log_r(log_n)
+    x = _rand384(99 + log_n, 1 << log_n)
+    shards = nd.scatter_input(x, log_n, world, limbs=12)
+    recv = [torch.zeros(12 << (log_n - lp), dtype=torch.int32, device="cuda") for _ in range(world)]
+    for r in range(world):
+        d = torch.from_numpy(shards[r].view(np.int32)).cuda().view(-1)
+        ctx.fourstep_step1_peer(d, [t.data_ptr() for t in recv], log_n, lr, lp, r)
+    torch.cuda.synchronize()
+    outs = []
+    for r in range(world):
+        ctx.fourstep_step2(recv[r], log_n, lr, lp, r)
+        torch.cuda.synchronize()
+        outs.append(recv[r].cpu().numpy().view(np.uint32).reshape(-1, 12))
+    assert np.array_equal(nd.gather_output(outs, log_n, world, lr, limbs=12), co.ntt384(x, p, g, threads=8))
+
+
+def test_host_buffers_pinned_and_pageable(env):
+    from oracle import c_oracle as co
+
+    torch, ctx, (p, g) = env
+    for log_n, batch in ((5, 3), (12, 2), (16, 1)):
+        x = _rand384(7 + log_n, batch << log_n)
+        want = np.concatenate([co.ntt384(x[b << log_n:(b + 1) << log_n], p, g, threads=4) for b in range(batch)])
+        assert np.array_equal(ctx.forward_host(x, log_n, batch).reshape(-1, 12), want)  # pageable: staged copies
+        h_in = torch.from_numpy(x.view(np.int32).copy()).pin_memory()
+        h_out = torch.zeros_like(h_in).pin_memory()
+        got = ctx.forward_host(h_in.numpy().view(np.uint32), log_n, batch, out=h_out.numpy().view(np.uint32))
+        assert np.array_equal(got.reshape(-1, 12), want)  # pinned: zero-copy end passes
+        back = ctx.inverse_host(h_out.numpy().view(np.uint32), log_n, batch, out=h_out.numpy().view(np.uint32))
+        assert np.array_equal(back.reshape(-1, 12), x)
+
+
+def test_coset_transforms_and_fused_pointwise_product(env):
+    """coset_forward = NTT of x[j] * s^j; coset_inverse undoes it; forward_mul multiplies the outputs by a
+    Montgomery-form vector inside the last pass."""
+    from oracle import c_oracle as co
+
+    torch, ctx, (p, g) = env
+    s = 0x1234567 * (1 << 300) + 12345
+    R = 1 << 384
+    for log_n, batch in ((3, 2), (10, 1), (13, 2)):
+        n = 1 << log_n
+        x = _rand384(300 + log_n, batch << log_n)
+        xi = _to_ints(x)
+        pre = _to_limbs([v * pow(s, j % n, p) % p for j, v in enumerate(xi)])
+        want = np.concatenate([co.ntt384(pre[b << log_n:(b + 1) << log_n], p, g, threads=4) for b in range(batch)])
+        got = _run(torch, ctx.coset_forward, x, log_n, s, batch)
+        assert np.array_equal(got, want), log_n
+        assert np.array_equal(_run(torch, ctx.coset_inverse, got, log_n, s, batch), x), log_n
+        # fused pointwise product: outputs times m (given in Montgomery form)
+        m = _to_ints(_rand384(900 + log_n, batch << log_n))
+        d = torch.from_numpy(x.view(np.int32).copy()).cuda()
+        dm = torch.from_numpy(_to_limbs([v * R % p for v in m]).view(np.int32)).cuda()
+        ctx.forward_mul(d, dm, log_n, batch)
+        torch.cuda.synchronize()
+        plain = np.concatenate([co.ntt384(x[b << log_n:(b + 1) << log_n], p, g, threads=4) for b in range(batch)])
+        want_mul = _to_limbs([a * b % p for a, b in zip(_to_ints(plain), m)])
+        assert np.array_equal(d.cpu().numpy().view(np.uint32).reshape(-1, 12), want_mul), log_n
