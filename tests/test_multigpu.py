@@ -163,6 +163,54 @@ dist.destroy_process_group()
 '''
 
 
+_WORKER_384 = r'''
+import os, sys
+sys.path.insert(0, os.environ["NTT_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from ntt_b200 import dist as nd
+from ntt_b200.api import Ntt384, FIELDS384
+from oracle import c_oracle as co
+rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr_)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
+# 384-bit containers over every GPU of the box (BLS12-377 Fq): the same FourStep driver, the 12-limb instances of
+# the pass kernels; NCCL all-to-all and the fused peer-store exchange with the synchronisation inside the kernels
+p, g = FIELDS384["bls12_377_fq"]
+ctx = Ntt384("bls12_377_fq", max_log_n=22, device=lr_)
+def rand384(seed, n):
+    x = np.random.default_rng(seed).integers(0, 1 << 32, size=(n, 12), dtype=np.uint64).astype(np.uint32)
+    x[:, 11] &= 0x00FFFFFF
+    return x
+for fused, barrier in ((False, "nccl"), (True, "nccl"), (True, "kernel")):
+  for log_n in (14, 20):
+    x = rand384(384 + log_n, 1 << log_n)                       # same on every rank
+    shard = nd.scatter_input(x, log_n, world, limbs=12)[rank]
+    fs = nd.FourStep(ctx, log_n, world, rank, fused=fused, barrier=barrier).load_shard(torch.from_numpy(shard.view(np.int32)).cuda().view(-1))
+    out = fs.forward().clone()
+    torch.cuda.synchronize()
+    gathered = [torch.empty_like(out) for _ in range(world)]
+    dist.all_gather(gathered, out)
+    if rank == 0:
+        X = nd.gather_output([t.cpu().numpy().view(np.uint32).reshape(-1, 12) for t in gathered], log_n, world, limbs=12)
+        assert np.array_equal(X, co.ntt384(x, p, g, threads=8)), f"384-bit four-step 2^{log_n} over {world} GPUs (fused={fused}) differs from the oracle"
+    back = fs.inverse().clone()
+    torch.cuda.synchronize()
+    assert np.array_equal(back.cpu().numpy().view(np.uint32).reshape(-1, 12), shard), f"inverse(forward(shard)) != shard (fused={fused}, 2^{log_n})"
+    for _ in range(4):
+        fs.forward(); fs.inverse()
+    torch.cuda.synchronize()
+    src = fs.a if not fused else (fs.a if fs._cur == 0 else fs.b)
+    assert np.array_equal(src.cpu().numpy().view(np.uint32).reshape(-1, 12), shard)
+    dist.barrier()
+    fs.check()
+    if fused:
+        fs.close()
+if rank == 0:
+    print("MULTIGPU384_OK", world)
+dist.destroy_process_group()
+'''
+
+
 def _run_workers(tmp_path, source, world, port, timeout=1500):
     script = tmp_path / "worker.py"
     script.write_text(source)
@@ -197,6 +245,19 @@ def test_config5_2p28_over_8_gpus_closed_form(tmp_path):
     out = _run_workers(tmp_path, _WORKER_28, 8, 29651)
     assert out.returncode == 0, (out.stdout[-1500:] + out.stderr[-3000:])
     assert "MULTIGPU28_OK" in out.stdout
+
+
+def test_384_bit_fourstep_over_all_gpus(tmp_path):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("needs CUDA")
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("single-GPU box: covered by the emulated ranks of tests/test_gpu_384.py")
+    out = _run_workers(tmp_path, _WORKER_384, 1 << (n.bit_length() - 1), 29661)
+    assert out.returncode == 0, (out.stdout[-1500:] + out.stderr[-3000:])
+    assert "MULTIGPU384_OK" in out.stdout
 
 
 def test_fourstep_and_batch_over_nccl(tmp_path):
