@@ -431,6 +431,73 @@ def _config5(torch, dist, np, args, world, rank, local_rank, p, g, stream):
             "checked": "sampled X[k] == c(h^n-1)/(h w^k-1) on every rank"}
 
 
+def _other_widths(torch, local_rank, steps):
+    """SURVEY 8f row 4 made driver-visible (N = 1 only): the 64-bit (Goldilocks) and 384-bit (BLS12-377 Fq)
+    instances of the same path, device-timed on synthetic canonical data, each with the roofline figures that
+    bound it.  Correctness of these widths is the GPU test suite's job (tests/test_gpu_64.py, test_gpu_384.py);
+    here X[0] = sum x is checked for the 64-bit transform as a cheap guard."""
+    from ntt_b200.api import Ntt384
+    from ntt_b200.api64 import Ntt64, plan_describe64
+
+    hbm_peak, _ = _peaks()
+    int_peak, _ = _int_peak()
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    log_n = 24
+    p64 = 0xFFFFFFFF00000001
+    c64 = Ntt64("goldilocks", max_log_n=log_n, device=local_rank)
+    d = torch.randint(0, 1 << 62, (1 << log_n,), dtype=torch.int64, device="cuda")
+    lo = int((d & 0xFFFFFFFF).sum().item())
+    hi = int((d >> 32).sum().item())
+    want0 = (lo + (hi << 32)) % p64
+    chk = d.clone()
+    c64.forward(chk, log_n)
+    got0 = int(chk[0].item()) & ((1 << 64) - 1)
+    if got0 != want0:
+        raise AssertionError("bench: 64-bit X[0] != sum of the inputs")
+    del chk
+    launches0 = c64.launch_count
+    ms = timed(lambda: c64.forward(d, log_n))
+    passes = (c64.launch_count - launches0) / (steps + 3)
+    n = 1 << log_n
+    out["goldilocks_64bit"] = {
+        "workload": f"2^{log_n}-point forward NTT, p = 2^64 - 2^32 + 1, one u64 per element", "ms_per_step": ms,
+        "value": n / ms * 1e3, "unit": UNIT, "G_butterflies_s": n / 2 * log_n / ms / 1e6, "passes_per_step": passes,
+        "roofline_hbm": {"achieved": 16.0 * n * passes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": 16.0 * n * passes / ms / 1e6 / hbm_peak, "bytes": "16 B per element per pass"},
+        "bound": "integer ALU issue (add/sub/reduce of 64-bit residues on 32-bit lanes: ~42 instructions per "
+                 "butterfly, ALU pipe 60-72 % busy, HBM 13-39 % per pass: profiles/r02_ncu_summary_64.json)",
+        "checked": "X[0] == sum x mod p"}
+    c64.close()
+    del d
+    log_n = 22
+    c384 = Ntt384("bls12_377_fq", max_log_n=log_n, device=local_rank)
+    d = torch.randint(0, 2**31 - 1, (1 << log_n, 12), dtype=torch.int32, device="cuda")
+    d[:, 11] &= 0x00FFFFFF
+    d = d.view(-1)
+    ms = timed(lambda: c384.forward(d, log_n))
+    n = 1 << log_n
+    macs = (n / 2) * log_n * (2 * 12 * 12 + 12)
+    out["bls12_377_fq_384bit"] = {
+        "workload": f"2^{log_n}-point forward NTT, 12 x u32 limbs per element", "ms_per_step": ms, "value": n / ms * 1e3,
+        "unit": UNIT, "roofline": {"bound": "int32-mul", "achieved": macs / ms / 1e9, "peak": int_peak, "unit": "T wide-MAC/s",
+                                   "frac": macs / ms / 1e9 / int_peak, "work": "300 MACs x (n/2) log2 n modmuls"}}
+    c384.close()
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -567,6 +634,13 @@ def run_ours(args):
             raise
         except Exception as e:  # an extra key must never cost the headline line
             extra["config3"] = {"error": repr(e)[:200]}
+        if world == 1:
+            try:
+                extra["other_widths"] = _other_widths(torch, local_rank, max(3, min(args.steps, 10)))
+            except AssertionError:
+                raise
+            except Exception as e:
+                extra["other_widths"] = {"error": repr(e)[:200]}
         if world == 8 and FIELD == "bn254_fr":
             try:
                 if fs is not None:
@@ -657,9 +731,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the config3 / config5 extra keys")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of fused peer stores")
-    ap.add_argument("--barrier", choices=("kernel", "flags", "nccl"), default="kernel",
-                    help="multi-GPU fused path: synchronisation folded into the pass kernels (default), a one-warp "
-                         "peer-memory barrier kernel, or a one-element NCCL all-reduce")
+    ap.add_argument("--barrier", choices=("kernel", "flags", "nccl"), default="flags",
+                    help="multi-GPU fused path: a one-warp peer-memory barrier kernel between the steps (default; fastest at "
+                         "8 GPUs, profiles/r02_diag_8gpu_b.json), synchronisation folded into the pass kernels, or a "
+                         "one-element NCCL all-reduce")
     ap.add_argument("--log-r", type=int, default=0, help="multi-GPU: rows = 2^log_r of the four-step view (0: automatic)")
     ap.add_argument("--field", default="bn254_fr", choices=["bn254_fr", "bls12_381_fr"])
     ap.add_argument("--log-n", type=int, default=24, help="transform size (default: the BASELINE metric's 2^24)")

@@ -124,14 +124,16 @@ class FourStep:
     fused=True : the exchange is the store phase of step 1's last kernel -- every output element
                  goes straight into the destination rank's receive buffer over NVLink
                  (peer-mapped memory shared through CUDA IPC); only a barrier separates the steps.
-    barrier    : how the fused path separates the steps.  "kernel" (default): no barrier launch at all --
-                 step 1's last kernel publishes an epoch from its last CTA, step 2's first kernel starts
-                 with every CTA waiting for all ranks' epochs (ntt256_ctx_set_peer_sync); "flags": the
-                 one-warp barrier kernel ntt256_peer_barrier; "nccl": a one-element all-reduce.
+    barrier    : how the fused path separates the steps.  "flags" (default): the one-warp barrier kernel
+                 ntt256_peer_barrier between the steps (the kernel boundary flushes step 1's peer stores);
+                 "kernel": no barrier launch at all -- step 1's last kernel publishes an epoch from its last
+                 CTA (one system-scope fence per CTA), step 2's first kernel starts with every CTA waiting for
+                 all ranks' epochs (ntt256_ctx_set_peer_sync); "nccl": a one-element all-reduce.  Measured
+                 at 2^24 on 8 B200 (profiles/r02_diag_8gpu_b.json): 489 / 526 / 507 us per transform.
     """
 
     def __init__(self, ctx, log_n: int, world: int, rank: int, log_r: int | None = None, group=None,
-                 fused: bool = False, barrier: str = "kernel"):
+                 fused: bool = False, barrier: str = "flags"):
         self.ctx, self.log_n, self.world, self.rank, self.group = ctx, log_n, world, rank, group
         self.log_p = _log2(world)
         self.log_r = default_log_r(log_n) if log_r is None else log_r

@@ -48,8 +48,19 @@ res["step2_us"] = timed(lambda: ctx.fourstep_step2(fs.b, log_n, lr, lp, rank))
 res["allreduce_us"] = timed(lambda: dist.all_reduce(flag))
 res["step1_peer_allreduce_us"] = timed(s1_peer_ar)
 res["full_again_us"] = timed(fs.forward)
+dist.barrier()
+fs.close()
+# the same transform with the other two ways of separating the steps
+for name in ("flags", "nccl"):
+    f2 = FourStep(ctx, log_n, world, rank, fused=True, barrier=name)
+    f2.load_shard(torch.randint(0, 2**28, ((1 << log_n) // world * 8,), dtype=torch.int32, device="cuda"))
+    res[f"full_{name}_barrier_us"] = timed(f2.forward)
+    dist.barrier()
+    f2.close()
+f3 = FourStep(ctx, log_n, world, rank, fused=False)
+f3.load_shard(torch.randint(0, 2**28, ((1 << log_n) // world * 8,), dtype=torch.int32, device="cuda"))
+res["full_nccl_all_to_all_us"] = timed(f3.forward)
 if rank == 0:
     print(json.dumps(res), flush=True)
 dist.barrier()
-fs.close()
 dist.destroy_process_group()
