@@ -15,7 +15,9 @@
  *     32 bytes, canonical residue in [0, p), NOT in Montgomery form (on a little-endian host the
  *     same bytes are the 4 x u64 limb layout of arkworks / blst / bellman field elements; data in
  *     Montgomery form can be passed as is -- the transform is linear, see ntt256_vec_mul for the
- *     one operation where the form matters);
+ *     one operation where the form matters).  CONTRACT: every input element must be a canonical
+ *     residue (< p), as cgbn_mem_t data in the reference is; nothing re-reduces the caller's data,
+ *     and values >= p give unspecified (not merely unreduced) results;
  *   - `prime` and `omega` are 8-limb host values; `omega` is the multiplicative GENERATOR g and
  *     the callee derives w_n = g^((p-1)/n) (big-num.cu:128-134, 292-296);
  *   - X[k] = sum_j x[j] * w_n^(jk) mod p (CPU oracle NTT(), big-num.cu:37-55).
