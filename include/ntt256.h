@@ -84,6 +84,10 @@ int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes);
  * tables right now and, through *streamed_bytes (may be NULL), the streamed arrays' share of it. */
 int ntt256_ctx_set_stream_twiddle_budget(ntt256_ctx* ctx, size_t total_bytes);
 size_t ntt256_ctx_table_bytes(const ntt256_ctx* ctx, size_t* streamed_bytes);
+/* The pass kernels of a transform are launched with programmatic stream serialization (default on): pass i+1
+ * becomes resident and does its index arithmetic while pass i drains its last wave, and touches no data before
+ * pass i has completed.  enable = 0 restores plain stream-ordered launches (same results). */
+int ntt256_ctx_set_dependent_launch(ntt256_ctx* ctx, int enable);
 /* Calls with batch * 2^log_n <= max_elements (default 2^17) are latency-bound and run on the
  * four-elements-per-thread kernel, those of at most half that on the two-elements-per-thread
  * kernel (more, shorter threads); 0 keeps every call on the throughput kernel. */

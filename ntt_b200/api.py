@@ -108,6 +108,10 @@ class Ntt256:
         """Force the pass kernel with 2^log2_elements (1..3) elements per thread; 0 = automatic."""
         self._check(self._L.ntt256_ctx_set_elements_per_thread(self._h, log2_elements))
 
+    def set_dependent_launch(self, enable: bool):
+        """Programmatic dependent launch between the pass kernels (default on)."""
+        self._check(self._L.ntt256_ctx_set_dependent_launch(self._h, int(bool(enable))))
+
     def set_twiddle_mode(self, shoup: bool):
         """True: (w, floor(w 2^256/p)) tables and Shoup products (fields with p < 2^254); False: Montgomery."""
         self._check(self._L.ntt256_ctx_set_twiddle_mode(self._h, int(bool(shoup))))

@@ -71,6 +71,9 @@ struct ntt256_ctx {
   // multiplier-bound path the separate element-wise kernel (full occupancy, HBM at 80 %) is as fast as the
   // fused form from ~2^18 elements on, and the fused form only saves a launch (profiles/r02_companions.jsonl).
   int fuse_companions = -1;
+  // programmatic dependent launch between the pass kernels of a stream (a pass becomes resident, and computes its
+  // indices, while its predecessor drains its last wave)
+  bool use_pdl = true;
   std::map<int, uint4*> loc_scaled;       // log_n -> (1/n) * loc[] : folds the inverse scaling into a round twiddle
   // streamed pass-twiddle arrays, keyed by (plan id, pass index, direction)
   struct TwStream {
@@ -254,14 +257,14 @@ struct FuseSpec {  // element-wise companions fused into the first / last pass (
 
 // The pass kernel for 2^group_bits elements per thread; FZ instances only for launches that carry companions.
 void launch_pass(bool shoup, int group_bits, bool dense, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream,
-                 const uint4* in, uint4* out, const PassArgs& A) {
+                 const uint4* in, uint4* out, const PassArgs& A, bool pdl) {
   const bool fz = A.in_scale || A.out_scale || A.out_mul;
   if (shoup) {
-    if (fz) launch_pass_inst<true, true>(group_bits, dense, grid, threads, smem, stream, in, out, A);
-    else launch_pass_inst<true, false>(group_bits, dense, grid, threads, smem, stream, in, out, A);
+    if (fz) launch_pass_inst<true, true>(group_bits, dense, grid, threads, smem, stream, in, out, A, pdl);
+    else launch_pass_inst<true, false>(group_bits, dense, grid, threads, smem, stream, in, out, A, pdl);
   } else {
-    if (fz) launch_pass_inst<false, true>(group_bits, dense, grid, threads, smem, stream, in, out, A);
-    else launch_pass_inst<false, false>(group_bits, dense, grid, threads, smem, stream, in, out, A);
+    if (fz) launch_pass_inst<false, true>(group_bits, dense, grid, threads, smem, stream, in, out, A, pdl);
+    else launch_pass_inst<false, false>(group_bits, dense, grid, threads, smem, stream, in, out, A, pdl);
   }
 }
 
@@ -362,7 +365,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
             const int Tg = G.pd.T;
             dim3 ggrid((unsigned)(1ull << G.pd.nblk_bits), 1, 1);
             launch_pass(sh, plan.group_bits, ctx->dense_pass4, ggrid, 1u << (Tg - plan.group_bits), (size_t)32 << Tg, stream,
-                        (const uint4*)d_data, (uint4*)d_data, G);
+                        (const uint4*)d_data, (uint4*)d_data, G, false);
             ++ctx->launches;
             CTX_CUDA(cudaGetLastError());
             // one-off: the array may be read from other streams by later calls
@@ -414,7 +417,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
     // first pass may read from `src_first`, last pass may write to `dst_last` (host-mapped buffers)
     const uint4* pin = (i == 0 && io && io->src_first) ? (const uint4*)io->src_first : (const uint4*)d_data;
     uint4* pout = (i + 1 == plan.passes.size() && io && io->dst_last) ? (uint4*)io->dst_last : (uint4*)d_data;
-    launch_pass(sh, GB, ctx->dense_pass4, grid, threads, smem, stream, pin, pout, A);
+    launch_pass(sh, GB, ctx->dense_pass4, grid, threads, smem, stream, pin, pout, A, ctx->use_pdl);
     ++ctx->launches;
     CTX_CUDA(cudaGetLastError());
   }
@@ -1278,6 +1281,12 @@ int ntt256_ctx_set_elements_per_thread(ntt256_ctx* ctx, int log2_elements) {
   return NTT256_OK;
 }
 
+int ntt256_ctx_set_dependent_launch(ntt256_ctx* ctx, int enable) {
+  if (!ctx) return NTT256_ERR_ARG;
+  ctx->use_pdl = enable != 0;
+  return NTT256_OK;
+}
+
 int ntt256_ctx_set_dense_pass4(ntt256_ctx* ctx, int enable) {
   if (!ctx) return NTT256_ERR_ARG;
   ctx->dense_pass4 = enable != 0;
@@ -1301,6 +1310,11 @@ struct PeerBarrierArgs {
 
 // Thread r: publish `epoch` in rank r's slot [rank], then wait for rank r's epoch in the local slot [r].
 __global__ void peer_barrier_kernel(const __grid_constant__ PeerBarrierArgs A) {
+  // programmatic dependent launch: the pass kernel behind this barrier may become resident now (it waits for this
+  // kernel's completion before it touches data); this kernel itself waits for its predecessor -- step 1's last
+  // pass and all its peer stores -- before it publishes anything
+  grid_dependency_launch_dependents();
+  grid_dependency_wait();
   const int r = threadIdx.x;
   if (r >= A.nranks) return;
   constexpr int kSlotBase = kSyncSlotBase;  // flags start at byte 256 (the first words carry the IPC check stamp)
@@ -1335,7 +1349,18 @@ int ntt256_peer_barrier(int device, void* const* flag_bufs, int nranks, int rank
   A.timeout_ns = g_barrier_timeout_ns;
   A.nranks = nranks;
   A.rank = rank;
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(A);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, 1, 1);
+    cfg.blockDim = dim3(32, 1, 1);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, peer_barrier_kernel, A);
+  }
   return cudaGetLastError() == cudaSuccess ? NTT256_OK : NTT256_ERR_CUDA;
 }
 

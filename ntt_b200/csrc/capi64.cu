@@ -288,12 +288,29 @@ int get_plan(ntt64_ctx* ctx, int log_n, int batch, const Plan** out, const ntt64
   return NTT256_OK;
 }
 
+template <class K>
+void launch_one64(K kernel, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const u64* in, u64* out,
+                  const PassArgs64& A) {
+  // programmatic stream serialization: the pass becomes resident while its predecessor drains (the kernels wait
+  // with griddepcontrol.wait before they touch data)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, in, out, A);
+}
 template <bool GL, int K16>
 void launch_pass_k(int gb, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const u64* in, u64* out,
                    const PassArgs64& A) {
-  if (gb == 4 && threads <= 256) ntt64_pass16d_kernel<GL, K16><<<grid, threads, smem, stream>>>(in, out, A);
-  else if (gb == 4) ntt64_pass16_kernel<GL, K16><<<grid, threads, smem, stream>>>(in, out, A);
-  else ntt64_pass4_kernel<GL, K16><<<grid, threads, smem, stream>>>(in, out, A);
+  if (gb == 4 && threads <= 256) launch_one64(ntt64_pass16d_kernel<GL, K16>, grid, threads, smem, stream, in, out, A);
+  else if (gb == 4) launch_one64(ntt64_pass16_kernel<GL, K16>, grid, threads, smem, stream, in, out, A);
+  else launch_one64(ntt64_pass4_kernel<GL, K16>, grid, threads, smem, stream, in, out, A);
 }
 // k16: 13 / 3 select the Goldilocks instances whose constant twiddles are shifts (w_16 = 2^(12 k16)); 0 = products
 void launch_pass(bool gl, int k16, int gb, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const u64* in,

@@ -13,6 +13,7 @@
 
 #include "field64.cuh"
 #include "kernel_common.cuh"
+#include "ntt_pass_generic.cuh"
 #include "plan.h"
 
 namespace ntt64 {
@@ -123,6 +124,9 @@ NTT_DEV void ntt_pass_body64(const u64* data_in, u64* data_out, const PassArgs64
   u64 x[NE];
   const int lowp = T - d;
 
+  // programmatic dependent launch (see ntt_pass_generic.cuh): nothing above touches mutable data -- the index
+  // tables are written once, at plan creation
+  ntt256::grid_dependency_wait();
   for (int r = 0; r < pd.nrounds; ++r) {
     const int sb = pd.round_sb[r];
     const int nb = pd.round_nb[r];
@@ -234,6 +238,7 @@ NTT_DEV void ntt_pass_body64(const u64* data_in, u64* data_out, const PassArgs64
       }
     }
   }
+  ntt256::grid_dependency_launch_dependents();
 }
 
 // Sixteen elements per thread: the throughput shape (tiles of up to 2^14 elements, <= 1024 threads).

@@ -142,6 +142,13 @@ NTT_DEV void round_compute(u32 (*x)[F::NL], const typename F::Args& A, const typ
 // is what small, latency-bound transforms need.
 // FZ: the launch carries element-wise companions (in_scale / out_scale / out_mul); plain transforms run the
 // FZ = false instances, whose code does not know about them.
+// Programmatic dependent launch (launches made with cudaLaunchAttributeProgrammaticStreamSerialization): the next
+// kernel of the stream may become resident while this one drains its last wave, and does its index arithmetic
+// there; it touches no data before grid_dependency_wait() returns, i.e. before this grid has completed and its
+// stores are visible.  Both are no-ops for ordinary launches.
+NTT_DEV void grid_dependency_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+NTT_DEV void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int GB, class F, bool FZ>
 NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename F::Args& A, u32* smem) {
   constexpr int NE = 1 << GB;
@@ -168,6 +175,7 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename
   const bool gen = (A.tw_gen_out != nullptr);
   const int lowp = T - d;  // lowest process bit
 
+  grid_dependency_wait();  // the previous kernel of the stream is complete: data, tables and flags may be touched
   if (A.sync_mode & 1) {
     // every rank's step 1 (and its peer stores into this rank's memory) must be complete
     if (tid < (u32)A.sync_nranks) {
@@ -355,6 +363,9 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename
       }
     }
   }
+  // Only now may the next kernel of the stream become resident: a trigger at the start would let the waiting CTAs
+  // of several future launches pile up on the SMs of a small grid and squeeze out the running one (2^16: 35 -> 60 us).
+  grid_dependency_launch_dependents();
   if (A.sync_mode & 2) {
     // this CTA's stores (peer memory included) are visible system-wide before it counts as arrived;
     // the last CTA of the grid tells every rank

@@ -9,9 +9,10 @@ struct FieldParams;
 template <class PARAMS, int NL, int TWS>
 struct PassArgsT;
 using PassArgs = PassArgsT<FieldParams, 8, 16>;
+// pdl: launch with cudaLaunchAttributeProgrammaticStreamSerialization (see grid_dependency_wait in ntt_pass_generic.cuh)
 template <bool SH, bool FZ>
 void launch_pass_inst(int group_bits, bool dense, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const uint4* in,
-                      uint4* out, const PassArgs& A);
+                      uint4* out, const PassArgs& A, bool pdl);
 // dense: four elements per thread on the three-CTAs-per-SM instance (ntt_pass4h_kernel) when the CTA fits it
 // raises the dynamic shared memory limit of the three kernels of one instance; false on a CUDA error
 template <bool SH, bool FZ>

@@ -683,6 +683,32 @@ def test_streamed_twiddle_arrays_stay_within_their_budget(torch_cuda):
     ctx.close()
 
 
+def test_dependent_launch_on_and_off_give_the_same_bits(torch_cuda):
+    """The pass kernels are launched with programmatic stream serialization (a pass becomes resident while its
+    predecessor drains, and waits before it touches data): same bits as plain launches for back-to-back
+    transforms of every kernel shape, forward and inverse, without host synchronisation in between."""
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = Ntt256("bn254_fr", max_log_n=22)
+    for log_n, batch in ((10, 1), (14, 1), (16, 1), (18, 1), (20, 1), (22, 1), (12, 50)):
+        x = co.splitmix_elements(batch << log_n, p, 31 + log_n)
+        want = co.ntt(x[: 1 << log_n], p, g, threads=8)
+        for enable in (True, False):
+            ctx.set_dependent_launch(enable)
+            d = torch.from_numpy(x.view(np.int32).copy()).cuda()
+            for _ in range(3):  # forward / inverse pairs back to back on the stream
+                ctx.forward(d, log_n, batch)
+                ctx.inverse(d, log_n, batch)
+            ctx.forward(d, log_n, batch)
+            torch.cuda.synchronize()
+            got = d.cpu().numpy().view(np.uint32).reshape(-1, 8)
+            assert np.array_equal(got[: 1 << log_n], want), (log_n, batch, enable)
+    ctx.close()
+
+
 def test_zero_copy_host_buffers(torch_cuda, ctxs):
     """Pinned host buffers: the first pass reads host memory and the last pass writes it directly
     (no staging copies).  Distinct and aliased in/out buffers, one pass and several passes."""
