@@ -178,6 +178,15 @@ void choose_shape(const ntt64_ctx* ctx, int log_n, int batch, int* tile_bits, in
     } else if (E <= (1ll << 19)) {
       T = std::min(10, log_n);
       g = std::min(g, 2);
+    } else if (ctx->tile_bits == kTileBits64 && ctx->coalesce_bits == kCoalesce64) {
+      // the plans the search finds under the default constraints are not equally good for every length
+      // (profiles/r02_ntt64_shape_sweep.jsonl): 2^19 and 2^22 lose a pass with runs of 8 elements instead of 16,
+      // batches of 2^16 (and 2^13) want 2^13-element tiles (two passes of eight stages instead of three)
+      if (log_n == 19 || log_n == 22) g = 3;
+      if ((log_n == 16 && batch >= 64) || log_n == 13) {
+        T = 13;
+        g = 2;
+      }
     }
   }
   if (T < gb) gb = 2;
