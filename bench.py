@@ -681,6 +681,7 @@ def run_ours(args):
     modmuls = (n / 2) * LOG_N
     macs_launch = modmuls * MACS_PER_MODMUL / world / max(passes, 1)
     int_achieved = macs_launch / (launch_ms / 1e3) / 1e12
+    issued = 107.0 if ctx.twiddle_mode == "shoup" else 132.0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -697,6 +698,14 @@ def run_ours(args):
                      "kernel": "ntt_pass_kernel", "launch_ms": launch_ms,
                      "algorithmic_macs_per_launch": macs_launch,
                      "work": "136 MACs x (n/2) log2 n modmuls (SURVEY 8d), whatever the multiplier really issues",
+                     # what the kernel really issues per product, in units of one wide multiply (4 fmaheavy clocks;
+                     # a low 32-bit multiply takes 2): Shoup product 99 + 16/2, Montgomery product 128 + 8/2
+                     "twiddle_mode": ctx.twiddle_mode,
+                     "issued_wide_equivalents_per_modmul": issued,
+                     "frac_issued": int_achieved / int_peak * issued / MACS_PER_MODMUL,
+                     "frac_issued_note": "share of the measured multiplier peak taken by the multiplies the kernel "
+                                         "executes (ncu: fmaheavy pipe 70 % busy, profiles/r02_ncu_stalls_by_opcode.md); "
+                                         "frac above is SURVEY 8d's algorithmic accounting",
                      "peak_source": int_src,
                      "frac_of_r01_denominator": int_achieved / 18.3,
                      "r01_denominator_note": "round 1 divided by 18.3 T/s, a figure its microbenchmark never measured "
