@@ -421,6 +421,17 @@ def _config5(torch, dist, np, args, world, rank, local_rank, p, g, stream):
     steps = 3
     ms = _timed(torch, dist, stream, fs.forward, steps) / steps
     nvlink_bytes = 32.0 * (n / world) * (world - 1) / world  # sent (= received) per GPU per transform
+    # the same transform on ONE B200 (it fits: 8 GiB of data), measured by scripts/time_large.py on this pool
+    one_gpu_ms, one_gpu_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_large_1gpu.jsonl")) as f:
+            for line in f:
+                row = json.loads(line)
+                if row.get("log_n") == log_n:
+                    one_gpu_ms = min(v for k, v in row.items() if k.endswith("_ms") and "montgomery" not in k)
+                    one_gpu_src = "profiles/r02_large_1gpu.jsonl (scripts/time_large.py, one B200; not re-measured by this run)"
+    except Exception:
+        pass
     fs.close()
     ctx.close()
     return {"workload": "2^28-point forward NTT, bn254_fr, four-step over 8 GPUs (1 GiB shard per GPU)",
@@ -428,6 +439,8 @@ def _config5(torch, dist, np, args, world, rank, local_rank, p, g, stream):
             "nvlink_bytes_per_gpu_per_step": nvlink_bytes,
             "nvlink_floor_ms": nvlink_bytes / 770e9 * 1e3,
             "int_floor_ms": (n / 2) * log_n * MACS_PER_MODMUL / world / (_int_peak()[0] * 1e12) * 1e3,
+            "single_gpu_ms": one_gpu_ms, "single_gpu_source": one_gpu_src,
+            "efficiency_vs_single_gpu": (one_gpu_ms / world / ms) if one_gpu_ms else None,
             "checked": "sampled X[k] == c(h^n-1)/(h w^k-1) on every rank"}
 
 

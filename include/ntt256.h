@@ -73,11 +73,11 @@ int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits);
 /* The first pass of a transform longer than 2^18 points needs twiddles w_n^e with a 2^log_n-wide
  * exponent range: either two table lookups and one extra product per element, or one coalesced
  * read from an n-entry array laid out like the pass's output (32*n bytes per (size, direction),
- * built on first use, kept in the context).  Arrays up to max_bytes are built automatically
- * (default: 1/16 of the device's memory, i.e. every n <= 2^28 on a 180 GB B200; when the
- * allocation fails the two-lookup path is used); 0 selects the two-lookup path always. */
+ * built on first use, kept in the context; 64*n bytes with Shoup pairs).  Arrays up to max_bytes are
+ * built automatically (default: 1/10 of the device's memory, i.e. every n <= 2^28 on a 180 GB B200;
+ * when the allocation fails the two-lookup path is used); 0 selects the two-lookup path always. */
 int ntt256_ctx_set_stream_twiddle_limit(ntt256_ctx* ctx, size_t max_bytes);
-/* All streamed arrays of a context together stay below total_bytes (default: 1/8 of the device's memory):
+/* All streamed arrays of a context together stay below total_bytes (default: 1/5 of the device's memory):
  * before a new one is built the least recently used ones are freed (cudaFree waits for the device, so a
  * launch that still reads one is never cut off); a transform whose array was dropped rebuilds it at its
  * next call.  ntt256_ctx_table_bytes returns the device memory the context holds in twiddle / coset
