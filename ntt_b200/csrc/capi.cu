@@ -83,7 +83,7 @@ struct ntt256_ctx {
   };
   std::map<std::tuple<unsigned long long, int, int>, TwStream> tw_streams;
   size_t tw_stream_limit = (size_t)1 << 30;   // largest array built automatically (bytes); 0 = never;
-                                              // set to 1/16 of the device's memory at creation
+                                              // set to 1/10 of the device's memory at creation
   size_t tw_stream_budget = (size_t)2 << 30;  // all cached arrays together; least recently used ones are dropped
                                               // to make room (set to 1/8 of the device's memory at creation)
   size_t tw_stream_bytes = 0;
