@@ -60,6 +60,11 @@ int ntt64_inverse_host(ntt64_ctx* ctx, const void* h_in, void* h_out, int log_n,
 int ntt64_coset_forward(ntt64_ctx* ctx, void* d_data, int log_n, int batch, uint64_t shift, ntt256_stream stream);
 int ntt64_coset_inverse(ntt64_ctx* ctx, void* d_data, int log_n, int batch, uint64_t shift, ntt256_stream stream);
 
+/* The multiplied-out shift^j table of a coset transform takes 8 * 2^log_n bytes (cached, four tables at most); above
+ * max_bytes (default 256 MiB) two factored tables of 2^(log_n/2) entries and a separate element-wise pass are used
+ * instead.  Drops the cached tables. */
+int ntt64_ctx_set_coset_table_limit(ntt64_ctx* ctx, size_t max_bytes);
+
 /* Element-wise product of n canonical elements, out = a*b mod p; out may alias a or b. */
 int ntt64_vec_mul(ntt64_ctx* ctx, void* d_out, const void* d_a, const void* d_b, unsigned long long n,
                   ntt256_stream stream);

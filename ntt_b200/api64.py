@@ -65,6 +65,10 @@ class Ntt64:
         """Goldilocks: constant twiddles of the register rounds by shifts (default) or on the multiplier."""
         self._check(self._L.ntt64_ctx_set_shift_twiddles(self._h, int(bool(enable))))
 
+    def set_coset_table_limit(self, max_bytes: int):
+        """Largest multiplied-out shift^j table; longer coset transforms use two factored tables + a separate pass."""
+        self._check(self._L.ntt64_ctx_set_coset_table_limit(self._h, int(max_bytes)))
+
     @staticmethod
     def _ptr(data, n_elements: int) -> int:
         if data.numel() * data.element_size() != n_elements * 8 or not data.is_cuda or not data.is_contiguous():

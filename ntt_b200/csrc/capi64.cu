@@ -86,6 +86,7 @@ struct ntt64_ctx {
   int tile_bits = kTileBits64, coalesce_bits = kCoalesce64;
   bool auto_shape = true;
   bool use_shift_twiddles = true;  // testing knob: false keeps the constant twiddles on the multiplier
+  size_t coset_direct_max = kCosetDirectMax64;  // largest multiplied-out shift^j table; longer transforms use two factored ones
   struct PlanTables {  // per pass: the index tables of PassArgs64 (one device allocation each)
     std::vector<u32*> thr;
     std::vector<uint2*> blk;
@@ -537,7 +538,7 @@ int get_coset(ntt64_ctx* ctx, u64 shift, int log_n, bool with_ninv, const ntt64_
   c.with_ninv = with_ninv ? 1 : 0;
   const u64 start = with_ninv ? ctx->hf.inv((1ull << log_n) % ctx->hf.p) : 1;
   int rc;
-  if (((size_t)8 << log_n) <= kCosetDirectMax64) {
+  if (((size_t)8 << log_n) <= ctx->coset_direct_max) {
     rc = build_power_table(ctx, &c.direct, shift, log_n, start, stream);
     if (rc) return rc;
   } else {
@@ -675,6 +676,16 @@ int ntt64_ctx_set_tuning(ntt64_ctx* ctx, int tile_bits, int coalesce_bits) {
   cudaDeviceSynchronize();
   ctx->plans.clear();  // loc_scaled tables depend on log_n only and stay valid
   free_plan_tables(ctx);
+  return NTT256_OK;
+}
+
+int ntt64_ctx_set_coset_table_limit(ntt64_ctx* ctx, size_t max_bytes) {
+  if (!ctx) return NTT256_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& c : ctx->cosets) free_coset(c);
+  ctx->cosets.clear();
+  ctx->coset_direct_max = max_bytes;
   return NTT256_OK;
 }
 

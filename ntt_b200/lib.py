@@ -45,7 +45,7 @@ EXPORTS384 = [
 # every symbol include/ntt64.h declares (the 64-bit companion API, same library)
 EXPORTS64 = [
     "ntt64_ctx_create", "ntt64_ctx_destroy", "ntt64_ctx_set_tuning", "ntt64_ctx_set_shift_twiddles", "ntt64_forward", "ntt64_inverse", "ntt64_forward_batch",
-    "ntt64_inverse_batch", "ntt64_forward_host", "ntt64_inverse_host", "ntt64_coset_forward", "ntt64_coset_inverse",
+    "ntt64_inverse_batch", "ntt64_forward_host", "ntt64_inverse_host", "ntt64_coset_forward", "ntt64_coset_inverse", "ntt64_ctx_set_coset_table_limit",
     "ntt64_vec_mul", "ntt64_launch_count", "ntt64_last_cuda_error", "ntt64_plan_describe",
 ]
 
@@ -163,6 +163,7 @@ def lib() -> ctypes.CDLL:
         L.ntt64_ctx_destroy.restype = None
         L.ntt64_ctx_set_tuning.argtypes = [vp, ci, ci]
         L.ntt64_ctx_set_shift_twiddles.argtypes = [vp, ci]
+        L.ntt64_ctx_set_coset_table_limit.argtypes = [vp, ctypes.c_size_t]
         for name in ("ntt64_forward", "ntt64_inverse"):
             getattr(L, name).argtypes = [vp, vp, ci, vp]
         for name in ("ntt64_forward_batch", "ntt64_inverse_batch"):

@@ -193,3 +193,25 @@ def test_output_location_and_geometric_input_helpers():
         for k in range(n):
             r, i = nd.output_location(k, log_n, world)
             assert np.array_equal(outs[r][i], X[k])
+
+
+def test_shard_layout_helpers_for_other_limb_counts():
+    """scatter_input / gather_input_layout and scatter_output_layout / gather_output are inverse pairs for 12-limb
+    (384-bit) elements as well, and move whole elements (every limb of an element travels together)."""
+    import numpy as np
+
+    from ntt_b200 import dist as nd
+
+    for limbs in (8, 12):
+        for log_n, world in ((6, 2), (8, 4), (10, 8)):
+            n = 1 << log_n
+            x = (np.arange(n, dtype=np.uint32)[:, None] * 16 + np.arange(limbs, dtype=np.uint32)[None, :]).astype(np.uint32)
+            shards = nd.scatter_input(x, log_n, world, limbs=limbs)
+            assert all(s.shape == (n // world, limbs) for s in shards)
+            assert all(np.array_equal(s % 16, np.tile(np.arange(limbs, dtype=np.uint32), (n // world, 1))) for s in shards)
+            assert np.array_equal(nd.gather_input_layout(shards, log_n, world, limbs=limbs), x)
+            outs = nd.scatter_output_layout(x, log_n, world, limbs=limbs)
+            assert np.array_equal(nd.gather_output(outs, log_n, world, limbs=limbs), x)
+            for k in (0, 1, n // 2 + 1, n - 1):
+                r, idx = nd.output_location(k, log_n, world)
+                assert np.array_equal(outs[r][idx], x[k])

@@ -214,6 +214,27 @@ def test_coset_and_pointwise(torch_cuda, ctxs, field, p, g):
     assert [int(v) for v in got] == want
 
 
+def test_coset_with_factored_tables(torch_cuda):
+    """Above the table limit the coset shift comes from two factored tables and a separate element-wise pass
+    (the inverse's low table carries 1/n): same bits as the oracle on pre-scaled inputs, and the round trip."""
+    from ntt_b200.api64 import Ntt64
+    from oracle import c_oracle as co
+
+    for field, p, g in (("goldilocks", GL_P, GL_G), ("ref29", REF_P, REF_G)):
+        ctx = Ntt64(field, max_log_n=16)
+        ctx.set_coset_table_limit(1024)  # 128 elements: everything below uses the factored tables
+        s = 0xABCDEF12345 % p
+        for log_n, batch in ((8, 3), (11, 1), (13, 2)):
+            n = 1 << log_n
+            x = co.splitmix64_elements(batch << log_n, p, 640 + log_n)
+            pre = np.array([(int(v) * pow(s, j % n, p)) % p for j, v in enumerate(x)], dtype=np.uint64)
+            got = _run(torch_cuda, ctx.coset_forward, x, log_n, s, batch)
+            for b in range(batch):
+                assert np.array_equal(got.reshape(batch, -1)[b], co.ntt64(pre.reshape(batch, -1)[b], p, g)), (field, log_n, b)
+            assert np.array_equal(_run(torch_cuda, ctx.coset_inverse, got, log_n, s, batch), x), (field, log_n)
+        ctx.close()
+
+
 def test_host_buffers_and_pipelined_batches(torch_cuda, ctxs):
     from oracle import c_oracle as co
 
