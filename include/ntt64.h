@@ -65,6 +65,21 @@ int ntt64_coset_inverse(ntt64_ctx* ctx, void* d_data, int log_n, int batch, uint
  * instead.  Drops the cached tables. */
 int ntt64_ctx_set_coset_table_limit(ntt64_ctx* ctx, size_t max_bytes);
 
+/* Multi-GPU four-step pieces, exactly as ntt256_fourstep_* (ntt256.h): 2^log_p ranks, n = 2^log_r rows x
+ * 2^(log_n - log_r) columns, rank = column block; step 1, one exchange of contiguous row blocks (an all-to-all, or
+ * none at all with *_peer, whose last pass stores every element straight into the destination rank's receive buffer
+ * through peer-mapped pointers; ntt256_ipc_* and ntt256_peer_barrier are width-independent), step 2.  The inverse pair
+ * consumes the forward's output shards and returns its input shards.  Goldilocks transforms of 2^28 .. 2^32 points
+ * are the use: a shard of 2^32 / 8 elements is 4 GiB. */
+int ntt64_fourstep_step1(ntt64_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank, ntt256_stream stream);
+int ntt64_fourstep_step1_peer(ntt64_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n, int log_r, int log_p,
+                              int rank, ntt256_stream stream);
+int ntt64_fourstep_step2(ntt64_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank, ntt256_stream stream);
+int ntt64_fourstep_inverse_step1(ntt64_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank, ntt256_stream stream);
+int ntt64_fourstep_inverse_step1_peer(ntt64_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n, int log_r,
+                                      int log_p, int rank, ntt256_stream stream);
+int ntt64_fourstep_inverse_step2(ntt64_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank, ntt256_stream stream);
+
 /* Element-wise product of n canonical elements, out = a*b mod p; out may alias a or b. */
 int ntt64_vec_mul(ntt64_ctx* ctx, void* d_out, const void* d_a, const void* d_b, unsigned long long n,
                   ntt256_stream stream);

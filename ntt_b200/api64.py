@@ -102,6 +102,38 @@ class Ntt64:
         self._check(self._L.ntt64_vec_mul(self._h, self._ptr(out, n), self._ptr(a, n), self._ptr(b, n), n, _stream_handle(stream)))
         return out
 
+    # ---- multi-GPU four-step pieces (same names and meaning as Ntt256's: ntt_b200.dist.FourStep drives either; use
+    # its default flag barrier -- the in-kernel rank synchronisation exists for the wide kernels only)
+    def set_peer_sync(self, flag_ptrs=None, rank: int = 0, timeout_s: float = 0.0):
+        if flag_ptrs is not None:
+            raise NotImplementedError("64-bit kernels: use FourStep(barrier='flags') or 'nccl'")
+
+    def _fs(self, fn, shard, log_n, log_r, log_p, rank, stream):
+        self._check(fn(self._h, self._ptr(shard, 1 << (log_n - log_p)), log_n, log_r, log_p, rank, _stream_handle(stream)))
+        return shard
+
+    def _fs_peer(self, fn, shard, peer_ptrs, log_n, log_r, log_p, rank, stream):
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(v) for v in peer_ptrs])
+        self._check(fn(self._h, self._ptr(shard, 1 << (log_n - log_p)), arr, log_n, log_r, log_p, rank, _stream_handle(stream)))
+        return shard
+
+    def fourstep_step1(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        return self._fs(self._L.ntt64_fourstep_step1, shard, log_n, log_r, log_p, rank, stream)
+
+    def fourstep_step1_peer(self, shard, peer_ptrs, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        return self._fs_peer(self._L.ntt64_fourstep_step1_peer, shard, peer_ptrs, log_n, log_r, log_p, rank, stream)
+
+    def fourstep_step2(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        return self._fs(self._L.ntt64_fourstep_step2, shard, log_n, log_r, log_p, rank, stream)
+
+    def fourstep_inverse_step1(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None, peer_ptrs=None):
+        if peer_ptrs is None:
+            return self._fs(self._L.ntt64_fourstep_inverse_step1, shard, log_n, log_r, log_p, rank, stream)
+        return self._fs_peer(self._L.ntt64_fourstep_inverse_step1_peer, shard, peer_ptrs, log_n, log_r, log_p, rank, stream)
+
+    def fourstep_inverse_step2(self, shard, log_n: int, log_r: int, log_p: int, rank: int, stream=None):
+        return self._fs(self._L.ntt64_fourstep_inverse_step2, shard, log_n, log_r, log_p, rank, stream)
+
     # ---- host buffers (numpy uint64 arrays; synchronous)
     def _host(self, fn, x: np.ndarray, log_n: int, batch: int, out):
         x = np.ascontiguousarray(x, dtype=np.uint64)

@@ -65,8 +65,10 @@ struct HostField64 {
 
 struct PlanKey64 {
   int log_n, tile_bits, group_bits, coalesce;
+  int kind = 0, log_r = 0, log_p = 0, rank = 0;  // kind 0: whole transform; 1..4: four-step pieces (plan.h FourStepKey)
   bool operator<(const PlanKey64& o) const {
-    return std::tie(log_n, tile_bits, group_bits, coalesce) < std::tie(o.log_n, o.tile_bits, o.group_bits, o.coalesce);
+    return std::tie(log_n, tile_bits, group_bits, coalesce, kind, log_r, log_p, rank) <
+           std::tie(o.log_n, o.tile_bits, o.group_bits, o.coalesce, o.kind, o.log_r, o.log_p, o.rank);
   }
 };
 
@@ -197,12 +199,16 @@ void choose_shape(const ntt64_ctx* ctx, int log_n, int batch, int* tile_bits, in
   *coalesce = g;
 }
 
-bool plan_for(int log_n, int T, int gb, int g, int max_log_n, Plan* plan) {
+bool plan_for(int log_n, int T, int gb, int g, int max_log_n, Plan* plan, const ntt256::FourStepKey* fk = nullptr) {
   PlanRequest req;
-  req.log_n = log_n;
-  req.tile_bits = T;
-  req.coalesce_bits = g;
-  req.max_log_n = max_log_n;
+  if (fk) {
+    req = ntt256::fourstep_request(*fk, T, g, max_log_n);
+  } else {
+    req.log_n = log_n;
+    req.tile_bits = T;
+    req.coalesce_bits = g;
+    req.max_log_n = max_log_n;
+  }
   req.group_bits = gb;
   req.max_tile_bits = kMaxTile64;
   bool ok = make_plan(req, plan);
@@ -275,14 +281,22 @@ int build_pass_tables(ntt64_ctx* ctx, const Plan& plan, ntt64_ctx::PlanTables* o
   return NTT256_OK;
 }
 
-int get_plan(ntt64_ctx* ctx, int log_n, int batch, const Plan** out, const ntt64_ctx::PlanTables** tabs) {
+int get_plan(ntt64_ctx* ctx, int log_n, int batch, const Plan** out, const ntt64_ctx::PlanTables** tabs,
+             const ntt256::FourStepKey* fk = nullptr) {
   PlanKey64 key;
   key.log_n = log_n;
-  choose_shape(ctx, log_n, batch, &key.tile_bits, &key.group_bits, &key.coalesce);
+  // a four-step piece works on the rank's 2^(log_n - log_p) local elements
+  choose_shape(ctx, fk ? log_n - fk->log_p : log_n, batch, &key.tile_bits, &key.group_bits, &key.coalesce);
+  if (fk) {
+    key.kind = fk->kind;
+    key.log_r = fk->log_r;
+    key.log_p = fk->log_p;
+    key.rank = fk->rank;
+  }
   auto it = ctx->plans.find(key);
   if (it == ctx->plans.end()) {
     Plan plan;
-    if (!plan_for(log_n, key.tile_bits, key.group_bits, key.coalesce, ctx->max_log_n, &plan)) return NTT256_ERR_PLAN;
+    if (!plan_for(log_n, key.tile_bits, key.group_bits, key.coalesce, ctx->max_log_n, &plan, fk)) return NTT256_ERR_PLAN;
     ntt64_ctx::PlanTables pt;
     int rc = build_pass_tables(ctx, plan, &pt);
     if (rc) {
@@ -349,6 +363,87 @@ struct Fuse64 {
   bool out_has_ninv = false;  // out_scale already carries 1/n
 };
 
+struct Peer64 {
+  const void* const* ptrs = nullptr;
+  int bits = 0, shift = 0, rank = 0;
+};
+
+// The passes of one plan over `batch` transforms starting at `p` (batch <= 65535); scale_log_n >= 0: multiply by
+// 2^-scale_log_n on the way (folded into a round-twiddle table when the last pass has two rounds).
+int run_plan64(ntt64_ctx* ctx, const Plan& plan, const ntt64_ctx::PlanTables& tabs, u64* p, unsigned long long batch_stride,
+               int batch, bool inverse, int scale_log_n, cudaStream_t stream, const Fuse64* fuse, const Peer64* peer) {
+  PassArgs64 A;
+  std::memset(&A, 0, sizeof(A));
+  A.f = ctx->fp;
+  A.om_hi = ctx->om_hi;
+  A.om_lo = ctx->om_lo;
+  A.loc = ctx->loc;
+  A.hi_bits = ctx->hi_bits;
+  A.lo_bits = ctx->lo_bits;
+  A.loc_bits = ctx->loc_bits;
+  A.inverse = inverse ? 1 : 0;
+  std::memcpy(A.c16, ctx->c16[inverse ? 1 : 0], sizeof(A.c16));
+  A.batch_stride = batch_stride;
+  A.scaled_round = -1;
+  const bool scale = scale_log_n >= 0;
+  const u64 ninv_tab = scale ? ctx->hf.tab(ctx->hf.inv((1ull << scale_log_n) % ctx->hf.p)) : 0;
+  A.scale = ninv_tab;
+  const u64* loc_scaled = nullptr;
+  if (scale && plan.passes.back().nrounds >= 2) {
+    // 1/n rides on the round twiddles of the last pass's first round (all sixteen elements of that round are
+    // multiplied, the one whose twiddle is 1 by 1/n itself)
+    auto it = ctx->loc_scaled.find(scale_log_n);
+    if (it == ctx->loc_scaled.end()) {
+      u64* tab = nullptr;
+      const unsigned long long count = 1ull << ctx->loc_bits;
+      CTX_CUDA(cudaMalloc((void**)&tab, count * 8));
+      if (ctx->hf.gl) table_scale_kernel64<true><<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(tab, ctx->loc, count, ctx->fp, ninv_tab);
+      else table_scale_kernel64<false><<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(tab, ctx->loc, count, ctx->fp, ninv_tab);
+      ++ctx->launches;
+      CTX_CUDA(cudaGetLastError());
+      CTX_CUDA(cudaStreamSynchronize(stream));  // one-off: later calls may use other streams
+      it = ctx->loc_scaled.emplace(scale_log_n, tab).first;
+    }
+    loc_scaled = it->second;
+  }
+  const int GB = plan.group_bits;
+  for (size_t i = 0; i < plan.passes.size(); ++i) {
+    A.pd = plan.passes[i];
+    A.scaled_round = -1;
+    A.loc_scaled = nullptr;
+    const bool last_pass = (i + 1 == plan.passes.size());
+    if (scale && last_pass) {
+      if (loc_scaled) {
+        A.scaled_round = 0;
+        A.loc_scaled = loc_scaled;
+      } else {
+        A.pd.scale_out = 1;
+      }
+    }
+    A.thr = tabs.thr[i];
+    A.blk = tabs.blk[i];
+    A.in_scale = (fuse && i == 0) ? fuse->in_scale : nullptr;
+    A.out_scale = (fuse && last_pass) ? fuse->out_scale : nullptr;
+    A.peer_bits = 0;
+    if (peer && last_pass) {
+      for (int r = 0; r < (1 << peer->bits); ++r) A.peer[r] = (unsigned long long)peer->ptrs[r];
+      A.peer_bits = peer->bits;
+      A.peer_shift = peer->shift;
+      A.peer_rank = peer->rank;
+    }
+    const int T = A.pd.T;
+    const unsigned long long nblk = 1ull << A.pd.nblk_bits;
+    if (nblk > 0x7fffffffull || batch > 65535) return NTT256_ERR_ARG;
+    dim3 grid((unsigned)nblk, (unsigned)batch, 1);
+    const unsigned threads = 1u << (T - GB);
+    const size_t smem = (size_t)8 << T;
+    launch_pass(ctx->hf.gl, ctx->use_shift_twiddles ? ctx->k16[inverse ? 1 : 0] : 0, GB, grid, threads, smem, stream, p, p, A);
+    ++ctx->launches;
+    CTX_CUDA(cudaGetLastError());
+  }
+  return NTT256_OK;
+}
+
 int transform(ntt64_ctx* ctx, void* d_data, int log_n, int batch, bool inverse, cudaStream_t stream,
               const Fuse64* fuse = nullptr) {
   if (!ctx || !d_data || log_n < 0 || log_n > ctx->max_log_n || batch < 1) return NTT256_ERR_ARG;
@@ -380,72 +475,39 @@ int transform(ntt64_ctx* ctx, void* d_data, int log_n, int batch, bool inverse, 
   const ntt64_ctx::PlanTables* tabs = nullptr;
   int rc = get_plan(ctx, log_n, batch, &plan, &tabs);
   if (rc) return rc;
-  PassArgs64 A;
-  std::memset(&A, 0, sizeof(A));
-  A.f = ctx->fp;
-  A.om_hi = ctx->om_hi;
-  A.om_lo = ctx->om_lo;
-  A.loc = ctx->loc;
-  A.hi_bits = ctx->hi_bits;
-  A.lo_bits = ctx->lo_bits;
-  A.loc_bits = ctx->loc_bits;
-  A.inverse = inverse ? 1 : 0;
-  std::memcpy(A.c16, ctx->c16[inverse ? 1 : 0], sizeof(A.c16));
-  A.batch_stride = 1ull << log_n;
-  A.scaled_round = -1;
-  A.scale = ninv_tab;
-  const u64* loc_scaled = nullptr;
-  if (scale && plan->passes.back().nrounds >= 2) {
-    // 1/n rides on the round twiddles of the last pass's first round (all sixteen elements of that round are
-    // multiplied, the one whose twiddle is 1 by 1/n itself)
-    auto it = ctx->loc_scaled.find(log_n);
-    if (it == ctx->loc_scaled.end()) {
-      u64* tab = nullptr;
-      const unsigned long long count = 1ull << ctx->loc_bits;
-      CTX_CUDA(cudaMalloc((void**)&tab, count * 8));
-      if (ctx->hf.gl) table_scale_kernel64<true><<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(tab, ctx->loc, count, ctx->fp, ninv_tab);
-      else table_scale_kernel64<false><<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(tab, ctx->loc, count, ctx->fp, ninv_tab);
-      ++ctx->launches;
-      CTX_CUDA(cudaGetLastError());
-      CTX_CUDA(cudaStreamSynchronize(stream));  // one-off: later calls may use other streams
-      it = ctx->loc_scaled.emplace(log_n, tab).first;
-    }
-    loc_scaled = it->second;
-  }
-  const int GB = plan->group_bits;
   const int kSlice = 65535;
   for (int b0 = 0; b0 < batch; b0 += kSlice) {
     const int nb = std::min(kSlice, batch - b0);
-    u64* p = (u64*)d_data + ((size_t)b0 << log_n);
-    for (size_t i = 0; i < plan->passes.size(); ++i) {
-      A.pd = plan->passes[i];
-      A.scaled_round = -1;
-      A.loc_scaled = nullptr;
-      const bool last_pass = (i + 1 == plan->passes.size());
-      if (scale && last_pass) {
-        if (loc_scaled) {
-          A.scaled_round = 0;
-          A.loc_scaled = loc_scaled;
-        } else {
-          A.pd.scale_out = 1;
-        }
-      }
-      A.thr = tabs->thr[i];
-      A.blk = tabs->blk[i];
-      A.in_scale = (fuse && i == 0) ? fuse->in_scale : nullptr;
-      A.out_scale = (fuse && last_pass) ? fuse->out_scale : nullptr;
-      const int T = A.pd.T;
-      const unsigned long long nblk = 1ull << A.pd.nblk_bits;
-      if (nblk > 0x7fffffffull) return NTT256_ERR_ARG;
-      dim3 grid((unsigned)nblk, (unsigned)nb, 1);
-      const unsigned threads = 1u << (T - GB);
-      const size_t smem = (size_t)8 << T;
-      launch_pass(ctx->hf.gl, ctx->use_shift_twiddles ? ctx->k16[inverse ? 1 : 0] : 0, GB, grid, threads, smem, stream, p, p, A);
-      ++ctx->launches;
-      CTX_CUDA(cudaGetLastError());
-    }
+    rc = run_plan64(ctx, *plan, *tabs, (u64*)d_data + ((size_t)b0 << log_n), 1ull << log_n, nb, inverse, scale ? log_n : -1,
+                    stream, fuse, nullptr);
+    if (rc) return rc;
   }
   return NTT256_OK;
+}
+
+// One local step of the multi-GPU four-step transform (kinds of plan.h FourStepKey); peer_recv != null: the last
+// pass stores straight into the ranks' receive buffers.
+int fourstep64(ntt64_ctx* ctx, int kind, void* d_shard, int log_n, int log_r, int log_p, int rank, cudaStream_t stream,
+               const void* const* peer_recv = nullptr) {
+  const bool inverse = kind >= 3;
+  const bool first_step = (kind == 1 || kind == 3);
+  if (!ctx || !d_shard || log_n > ctx->max_log_n || !ntt256::fourstep_args_ok(log_n, log_r, log_p, rank)) return NTT256_ERR_ARG;
+  CTX_CUDA(cudaSetDevice(ctx->device));
+  const ntt256::FourStepKey fk{kind, log_n, log_r, log_p, first_step ? rank : 0};
+  const Plan* plan = nullptr;
+  const ntt64_ctx::PlanTables* tabs = nullptr;
+  int rc = get_plan(ctx, log_n, 1, &plan, &tabs, &fk);
+  if (rc) return rc;
+  Peer64 ps;
+  if (peer_recv && log_p > 0) {
+    if (log_p > 3) return NTT256_ERR_ARG;
+    ps.ptrs = peer_recv;
+    ps.bits = log_p;
+    ps.shift = log_n - 2 * log_p;  // local index bits below the destination-rank field
+    ps.rank = rank;
+  }
+  return run_plan64(ctx, *plan, *tabs, (u64*)d_shard, 0, 1, inverse, kind == 4 ? log_n : -1, stream, nullptr,
+                    ps.bits ? &ps : nullptr);
 }
 
 int ensure_stage(ntt64_ctx* ctx, size_t bytes) {
@@ -712,6 +774,29 @@ int ntt64_forward_host(ntt64_ctx* ctx, const void* h_in, void* h_out, int log_n,
 }
 int ntt64_inverse_host(ntt64_ctx* ctx, const void* h_in, void* h_out, int log_n, int batch) {
   return transform_host(ctx, h_in, h_out, log_n, batch, true);
+}
+
+int ntt64_fourstep_step1(ntt64_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank, ntt256_stream stream) {
+  return fourstep64(ctx, 1, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream);
+}
+int ntt64_fourstep_step1_peer(ntt64_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n, int log_r, int log_p,
+                              int rank, ntt256_stream stream) {
+  if (!peer_recv) return NTT256_ERR_ARG;
+  return fourstep64(ctx, 1, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream, peer_recv);
+}
+int ntt64_fourstep_step2(ntt64_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank, ntt256_stream stream) {
+  return fourstep64(ctx, 2, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream);
+}
+int ntt64_fourstep_inverse_step1(ntt64_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank, ntt256_stream stream) {
+  return fourstep64(ctx, 3, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream);
+}
+int ntt64_fourstep_inverse_step1_peer(ntt64_ctx* ctx, void* d_shard, const void* const* peer_recv, int log_n, int log_r,
+                                      int log_p, int rank, ntt256_stream stream) {
+  if (!peer_recv) return NTT256_ERR_ARG;
+  return fourstep64(ctx, 3, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream, peer_recv);
+}
+int ntt64_fourstep_inverse_step2(ntt64_ctx* ctx, void* d_shard, int log_n, int log_r, int log_p, int rank, ntt256_stream stream) {
+  return fourstep64(ctx, 4, d_shard, log_n, log_r, log_p, rank, (cudaStream_t)stream);
 }
 
 int ntt64_coset_forward(ntt64_ctx* ctx, void* d_data, int log_n, int batch, uint64_t shift, ntt256_stream stream) {

@@ -49,6 +49,12 @@ struct PassArgs64 {
   //   blk[b]               .x = index of the tile's first element inside one transform, .y = the block's share of j_low
   const u32* thr;
   const uint2* blk;
+  // Fused exchange (multi-GPU four-step, last pass of step 1; same scheme as the wide kernels): when peer_bits > 0
+  // the tile is stored straight into the receive buffers of the destination ranks over NVLink (peer-mapped
+  // pointers): destination = top peer_bits of the local output index, remote index = (my rank << peer_shift) |
+  // (low peer_shift bits).
+  unsigned long long peer[8];
+  int peer_bits, peer_shift, peer_rank;
 };
 
 // K16 != 0 (Goldilocks only): w_16 = 2^(12 K16), the constant twiddles are shifts (field64.cuh gl_sub_mul_w16)
@@ -229,12 +235,25 @@ NTT_DEV void ntt_pass_body64(const u64* data_in, u64* data_out, const PassArgs64
       // a single-round pass loads and stores global memory in the same round: every thread of the CTA must
       // have loaded before any permuted store lands on another thread's input
       if (first) __syncthreads();
+      if (A.peer_bits == 0) {
 #pragma unroll
-      for (int u = 0; u < NE; ++u) {
-        u32 off = g0;
+        for (int u = 0; u < NE; ++u) {
+          u32 off = g0;
 #pragma unroll
-        for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
-        gbase[off] = x[u];
+          for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
+          gbase[off] = x[u];
+        }
+      } else {
+        const u32 lowmask = (1u << A.peer_shift) - 1u;
+        const u32 mine = (u32)A.peer_rank << A.peer_shift;
+#pragma unroll
+        for (int u = 0; u < NE; ++u) {
+          u32 off = (u32)base + g0;  // full local output index: block part + in-tile part
+#pragma unroll
+          for (int i = 0; i < GB; ++i) off += ((u >> i) & 1) ? st[i] : 0u;
+          u64* dst = reinterpret_cast<u64*>(A.peer[off >> A.peer_shift]) + (size_t)(mine | (off & lowmask));
+          *dst = x[u];
+        }
       }
     }
   }

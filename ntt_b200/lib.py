@@ -46,6 +46,8 @@ EXPORTS384 = [
 EXPORTS64 = [
     "ntt64_ctx_create", "ntt64_ctx_destroy", "ntt64_ctx_set_tuning", "ntt64_ctx_set_shift_twiddles", "ntt64_forward", "ntt64_inverse", "ntt64_forward_batch",
     "ntt64_inverse_batch", "ntt64_forward_host", "ntt64_inverse_host", "ntt64_coset_forward", "ntt64_coset_inverse", "ntt64_ctx_set_coset_table_limit",
+    "ntt64_fourstep_step1", "ntt64_fourstep_step1_peer", "ntt64_fourstep_step2", "ntt64_fourstep_inverse_step1",
+    "ntt64_fourstep_inverse_step1_peer", "ntt64_fourstep_inverse_step2",
     "ntt64_vec_mul", "ntt64_launch_count", "ntt64_last_cuda_error", "ntt64_plan_describe",
 ]
 
@@ -164,6 +166,10 @@ def lib() -> ctypes.CDLL:
         L.ntt64_ctx_set_tuning.argtypes = [vp, ci, ci]
         L.ntt64_ctx_set_shift_twiddles.argtypes = [vp, ci]
         L.ntt64_ctx_set_coset_table_limit.argtypes = [vp, ctypes.c_size_t]
+        for name in ("ntt64_fourstep_step1", "ntt64_fourstep_step2", "ntt64_fourstep_inverse_step1", "ntt64_fourstep_inverse_step2"):
+            getattr(L, name).argtypes = [vp, vp, ci, ci, ci, ci, vp]
+        for name in ("ntt64_fourstep_step1_peer", "ntt64_fourstep_inverse_step1_peer"):
+            getattr(L, name).argtypes = [vp, vp, ctypes.POINTER(vp), ci, ci, ci, ci, vp]
         for name in ("ntt64_forward", "ntt64_inverse"):
             getattr(L, name).argtypes = [vp, vp, ci, vp]
         for name in ("ntt64_forward_batch", "ntt64_inverse_batch"):

@@ -283,3 +283,59 @@ def test_linearity_and_checksum_at_2_26(torch_cuda):
     assert np.array_equal(_run(torch, ctx.inverse, A, log_n), a)
     del B
     ctx.close()
+
+
+@pytest.mark.parametrize("field,p,g", [("goldilocks", GL_P, GL_G), ("ref29", REF_P, REF_G)])
+@pytest.mark.parametrize("log_n,world", [(12, 1), (14, 2), (16, 8), (18, 4), (21, 8), (22, 2)])
+def test_fourstep_ranks_emulated_on_one_gpu(torch_cuda, ctxs, field, p, g, log_n, world):
+    """The 64-bit four-step pieces: scatter -> step 1 per rank -> the all-to-all by its host definition -> step 2 per
+    rank -> gather equals the single-transform oracle; the inverse pair takes the output shards back."""
+    from ntt_b200 import dist as nd
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    ctx = ctxs(field, 22)
+    log_p, log_r = world.bit_length() - 1, nd.default_log_r(log_n)
+    x = co.splitmix64_elements(1 << log_n, p, 40 + log_n)
+    want = co.ntt64(x, p, g, threads=8)
+
+    def each(fn, shards):
+        out = []
+        for r, sh in enumerate(shards):
+            d = torch.from_numpy(np.ascontiguousarray(sh).reshape(-1).view(np.int64)).cuda()
+            fn(d, log_n, log_r, log_p, r)
+            torch.cuda.synchronize()
+            out.append(d.cpu().numpy().view(np.uint64).reshape(-1, 1))
+        return out
+
+    ins = nd.scatter_input(x.reshape(-1, 1), log_n, world, log_r, limbs=1)
+    s2 = each(ctx.fourstep_step2, nd.exchange_reference(each(ctx.fourstep_step1, ins), world))
+    assert np.array_equal(nd.gather_output(s2, log_n, world, log_r, limbs=1).reshape(-1), want)
+    back = each(ctx.fourstep_inverse_step2, nd.exchange_reference(each(ctx.fourstep_inverse_step1, s2), world))
+    for r in range(world):
+        assert np.array_equal(back[r], ins[r]), r
+
+
+@pytest.mark.parametrize("log_n,world", [(14, 2), (18, 8)])
+def test_fused_peer_store_on_one_gpu(torch_cuda, ctxs, log_n, world):
+    """ntt64_fourstep_step1_peer with every rank's receive buffer on this GPU: the store phase of the butterfly
+    kernel delivers exactly what step 1 + all-to-all delivers."""
+    from ntt_b200 import dist as nd
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    ctx = ctxs("goldilocks", 22)
+    lp, lr = world.bit_length() - 1, nd.default_log_r(log_n)
+    x = co.splitmix64_elements(1 << log_n, GL_P, 99 + log_n)
+    shards = nd.scatter_input(x.reshape(-1, 1), log_n, world, limbs=1)
+    recv = [torch.zeros(1 << (log_n - lp), dtype=torch.int64, device="cuda") for _ in range(world)]
+    for r in range(world):
+        d = torch.from_numpy(np.ascontiguousarray(shards[r]).reshape(-1).view(np.int64)).cuda()
+        ctx.fourstep_step1_peer(d, [t.data_ptr() for t in recv], log_n, lr, lp, r)
+    torch.cuda.synchronize()
+    outs = []
+    for r in range(world):
+        ctx.fourstep_step2(recv[r], log_n, lr, lp, r)
+        torch.cuda.synchronize()
+        outs.append(recv[r].cpu().numpy().view(np.uint64).reshape(-1, 1))
+    assert np.array_equal(nd.gather_output(outs, log_n, world, lr, limbs=1).reshape(-1), co.ntt64(x, GL_P, GL_G, threads=8))

@@ -211,6 +211,50 @@ dist.destroy_process_group()
 '''
 
 
+_WORKER_64 = r'''
+import os, sys
+sys.path.insert(0, os.environ["NTT_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from ntt_b200 import dist as nd
+from ntt_b200.api64 import Ntt64, FIELDS64
+from oracle import c_oracle as co
+rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr_)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
+# 64-bit containers (Goldilocks) over every GPU of the box: the same FourStep driver; NCCL all-to-all and the fused
+# peer-store exchange behind the flag barrier
+p, g = FIELDS64["goldilocks"]
+ctx = Ntt64("goldilocks", max_log_n=24, device=lr_)
+for fused, barrier in ((False, "nccl"), (True, "nccl"), (True, "flags")):
+  for log_n in (14, 20, 24):
+    x = co.splitmix64_elements(1 << log_n, p, 64 + log_n)     # same on every rank
+    shard = nd.scatter_input(x.reshape(-1, 1), log_n, world, limbs=1)[rank].reshape(-1)
+    fs = nd.FourStep(ctx, log_n, world, rank, fused=fused, barrier=barrier).load_shard(torch.from_numpy(shard.view(np.int64)).cuda())
+    out = fs.forward().clone()
+    torch.cuda.synchronize()
+    gathered = [torch.empty_like(out) for _ in range(world)]
+    dist.all_gather(gathered, out)
+    if rank == 0:
+        X = nd.gather_output([t.cpu().numpy().view(np.uint64).reshape(-1, 1) for t in gathered], log_n, world, limbs=1).reshape(-1)
+        assert np.array_equal(X, co.ntt64(x, p, g, threads=16)), f"64-bit four-step 2^{log_n} over {world} GPUs (fused={fused}) differs from the oracle"
+    back = fs.inverse().clone()
+    torch.cuda.synchronize()
+    assert np.array_equal(back.cpu().numpy().view(np.uint64).reshape(-1), shard), f"inverse(forward(shard)) != shard (fused={fused}, 2^{log_n})"
+    for _ in range(4):
+        fs.forward(); fs.inverse()
+    torch.cuda.synchronize()
+    src = fs.a if not fused else (fs.a if fs._cur == 0 else fs.b)
+    assert np.array_equal(src.cpu().numpy().view(np.uint64).reshape(-1), shard)
+    dist.barrier()
+    fs.check()
+    if fused:
+        fs.close()
+if rank == 0:
+    print("MULTIGPU64_OK", world)
+dist.destroy_process_group()
+'''
+
+
 def _run_workers(tmp_path, source, world, port, timeout=1500):
     script = tmp_path / "worker.py"
     script.write_text(source)
@@ -258,6 +302,19 @@ def test_384_bit_fourstep_over_all_gpus(tmp_path):
     out = _run_workers(tmp_path, _WORKER_384, 1 << (n.bit_length() - 1), 29661)
     assert out.returncode == 0, (out.stdout[-1500:] + out.stderr[-3000:])
     assert "MULTIGPU384_OK" in out.stdout
+
+
+def test_64_bit_fourstep_over_all_gpus(tmp_path):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("needs CUDA")
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("single-GPU box: covered by the emulated ranks of tests/test_gpu_64.py")
+    out = _run_workers(tmp_path, _WORKER_64, 1 << (n.bit_length() - 1), 29671)
+    assert out.returncode == 0, (out.stdout[-1500:] + out.stderr[-3000:])
+    assert "MULTIGPU64_OK" in out.stdout
 
 
 def test_fourstep_and_batch_over_nccl(tmp_path):
