@@ -17,6 +17,7 @@
 #include "hostfield.h"
 #include "aux_kernels.cuh"
 #include "pass_launch.h"
+#include "pass_tables.h"
 #include "plan.h"
 
 using namespace ntt256;
@@ -101,6 +102,7 @@ struct ntt256_ctx {
   cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_done[3] = {nullptr, nullptr, nullptr},
               ev_out[3] = {nullptr, nullptr, nullptr};
   std::map<PlanKey, Plan> plans;
+  std::map<unsigned long long, PassTables> plan_tables;  // by Plan::id: the index tables of its passes (pass_tables.h)
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
   // rank synchronisation folded into the four-step passes (ntt256_ctx_set_peer_sync)
@@ -235,6 +237,12 @@ int get_plan(ntt256_ctx* ctx, const PlanKey& key, const Plan** out) {
     }
     if (!ok) return NTT256_ERR_PLAN;
     plan.id = ctx->next_plan_id++;
+    PassTables pt;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || build_pass_tables(plan, &pt) != cudaSuccess) {
+      ctx->last_err = "index tables of a plan (cudaMalloc / cudaMemcpy)";
+      return NTT256_ERR_CUDA;
+    }
+    ctx->plan_tables.emplace(plan.id, pt);
     it = ctx->plans.emplace(key, plan).first;
   }
   *out = &it->second;
@@ -334,8 +342,11 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
       loc_scaled = it->second;
     }
   }
+  const PassTables& tabs = ctx->plan_tables.at(plan.id);
   for (size_t i = 0; i < plan.passes.size(); ++i) {
     A.pd = plan.passes[i];
+    A.thr = tabs.thr[i];
+    A.blk = tabs.blk[i];
     A.scaled_round = -1;
     A.loc_scaled = nullptr;
     if (scale_log_n >= 0 && i + 1 == plan.passes.size()) {
@@ -836,6 +847,7 @@ void ntt256_ctx_destroy(ntt256_ctx* ctx) {
   }
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->sync_counter) cudaFree(ctx->sync_counter);
+  for (auto& kv : ctx->plan_tables) free_pass_tables(&kv.second);
   delete ctx;
 }
 
@@ -846,7 +858,11 @@ int ntt256_ctx_set_tuning(ntt256_ctx* ctx, int tile_bits, int coalesce_bits) {
   ctx->tile_bits = tile_bits;
   ctx->coalesce_bits = coalesce_bits;
   ctx->auto_tile = false;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
   ctx->plans.clear();
+  for (auto& kv : ctx->plan_tables) free_pass_tables(&kv.second);
+  ctx->plan_tables.clear();
   drop_tw_streams(ctx);
   return NTT256_OK;
 }

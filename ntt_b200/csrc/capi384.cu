@@ -18,6 +18,7 @@
 #include "../../include/ntt384.h"
 #include "hostfield_n.h"
 #include "ntt_kernels_n.cuh"
+#include "pass_tables.h"
 #include "plan.h"
 
 using namespace ntt256;
@@ -46,6 +47,8 @@ struct ntt384_ctx {
   bool ninv_ok[64] = {};
   int tile_bits = kTileBits384, coalesce_bits = kCoalesce384;
   std::map<std::tuple<int, int, int, int, int>, Plan> plans;  // by (kind, log_n, log_r, log_p, rank); kind 0 = whole transform
+  std::map<unsigned long long, PassTables> plan_tables;          // by Plan::id: the index tables of its passes
+  unsigned long long next_plan_id = 1;
   std::map<int, uint4*> loc_scaled;  // log_n -> (1/n) * loc[]
   struct Coset {
     U384 shift;  // plain
@@ -123,6 +126,13 @@ int get_plan(ntt384_ctx* ctx, const FourStepKey& key, const Plan** out) {
       ok = make_plan(req, &plan, 12);
     }
     if (!ok) return NTT256_ERR_PLAN;
+    plan.id = ctx->next_plan_id++;
+    PassTables pt;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || build_pass_tables(plan, &pt) != cudaSuccess) {
+      ctx->last_err = "index tables of a plan (cudaMalloc / cudaMemcpy)";
+      return NTT256_ERR_CUDA;
+    }
+    ctx->plan_tables.emplace(plan.id, pt);
     it = ctx->plans.emplace(k, plan).first;
   }
   *out = &it->second;
@@ -189,9 +199,12 @@ int run_plan(ntt384_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
     }
   }
   const bool fz = fuse && (fuse->in_scale || fuse->out_scale || fuse->out_mul);
+  const PassTables& tabs = ctx->plan_tables.at(plan.id);
   for (size_t i = 0; i < plan.passes.size(); ++i) {
     const bool last_pass = (i + 1 == plan.passes.size());
     A.pd = plan.passes[i];
+    A.thr = tabs.thr[i];
+    A.blk = tabs.blk[i];
     A.scaled_round = -1;
     A.loc_scaled = nullptr;
     if (scale_log_n >= 0 && last_pass) {
@@ -464,6 +477,7 @@ void ntt384_ctx_destroy(ntt384_ctx* ctx) {
   if (ctx->loc) cudaFree(ctx->loc);
   for (auto& kv : ctx->loc_scaled) cudaFree(kv.second);
   for (auto& c : ctx->cosets) cudaFree(c.direct);
+  for (auto& kv : ctx->plan_tables) free_pass_tables(&kv.second);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->sync_counter) cudaFree(ctx->sync_counter);
   delete ctx;
@@ -474,7 +488,11 @@ int ntt384_ctx_set_tuning(ntt384_ctx* ctx, int tile_bits, int coalesce_bits) {
     return NTT256_ERR_ARG;
   ctx->tile_bits = tile_bits;
   ctx->coalesce_bits = coalesce_bits;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
   ctx->plans.clear();  // loc_scaled tables depend on log_n only and stay valid
+  for (auto& kv : ctx->plan_tables) free_pass_tables(&kv.second);
+  ctx->plan_tables.clear();
   return NTT256_OK;
 }
 

@@ -16,6 +16,7 @@
 
 #include "../../include/ntt64.h"
 #include "ntt_kernels_64.cuh"
+#include "pass_tables.h"
 #include "plan.h"
 
 using namespace ntt64;
@@ -89,10 +90,7 @@ struct ntt64_ctx {
   bool auto_shape = true;
   bool use_shift_twiddles = true;  // testing knob: false keeps the constant twiddles on the multiplier
   size_t coset_direct_max = kCosetDirectMax64;  // largest multiplied-out shift^j table; longer transforms use two factored ones
-  struct PlanTables {  // per pass: the index tables of PassArgs64 (one device allocation each)
-    std::vector<u32*> thr;
-    std::vector<uint2*> blk;
-  };
+  typedef ntt256::PassTables PlanTables;  // per pass: the index tables of PassArgs64 (pass_tables.h)
   std::map<PlanKey64, Plan> plans;
   std::map<PlanKey64, PlanTables> plan_tables;
   std::map<int, u64*> loc_scaled;  // log_n -> (1/n) * loc[]
@@ -225,60 +223,9 @@ bool plan_for(int log_n, int T, int gb, int g, int max_log_n, Plan* plan, const 
   return ok;
 }
 
-u32 deposit_host(unsigned long long v, const int8_t* pos, int n) {
-  unsigned long long r = 0;
-  for (int i = 0; i < n; ++i) r |= ((v >> i) & 1ull) << pos[i];
-  return (u32)r;
-}
-u32 swz_host(u32 l) { return l ^ ((l >> 5) & 31u) ^ ((l >> 10) & 31u); }
-
 void free_plan_tables(ntt64_ctx* ctx) {
-  for (auto& kv : ctx->plan_tables) {
-    for (u32* p : kv.second.thr) cudaFree(p);
-    for (uint2* p : kv.second.blk) cudaFree(p);
-  }
+  for (auto& kv : ctx->plan_tables) ntt256::free_pass_tables(&kv.second);
   ctx->plan_tables.clear();
-}
-
-// The index tables a pass kernel looks up instead of depositing bits (layout: PassArgs64::thr / blk).
-int build_pass_tables(ntt64_ctx* ctx, const Plan& plan, ntt64_ctx::PlanTables* out) {
-  const int GB = plan.group_bits;
-  for (const ntt256::PassDesc& pd : plan.passes) {
-    const int T = pd.T, lowp = pd.T - pd.d;
-    const u32 t = 1u << (T - GB);
-    std::vector<u32> thr((size_t)(3 + pd.nrounds) * t);
-    for (u32 tid = 0; tid < t; ++tid) {
-      const u32 lam_first = deposit_host(tid, pd.tmap[0], T - GB);
-      const u32 lam_last = deposit_host(tid, pd.tmap[pd.nrounds - 1], T - GB);
-      thr[tid] = deposit_host(lam_first, pd.in_pos, T);
-      thr[t + tid] = deposit_host(lam_last, pd.out_pos, T);
-      u32 jl = 0;
-      for (int i = 0; i < lowp; ++i) jl += ((lam_last >> i) & 1u) * pd.wt_loc[i];
-      thr[2 * t + tid] = jl;
-      for (int r = 0; r < pd.nrounds; ++r) {
-        const u32 lam = deposit_host(tid, pd.tmap[r], T - GB);
-        thr[(size_t)(3 + r) * t + tid] = lam | (swz_host(lam) << 16);
-      }
-    }
-    const size_t nblk = (size_t)1 << pd.nblk_bits;
-    std::vector<uint2> blk(nblk);
-    for (size_t b = 0; b < nblk; ++b) {
-      u32 jl = pd.jlow_const;
-      for (int i = 0; i < pd.nblk_bits; ++i) jl += (u32)((b >> i) & 1) * pd.wt_blk[i];
-      blk[b] = make_uint2(deposit_host(b, pd.blk_pos, pd.nblk_bits), jl);
-    }
-    u32* d_thr = nullptr;
-    uint2* d_blk = nullptr;
-    CTX_CUDA(cudaMalloc((void**)&d_thr, thr.size() * 4));
-    out->thr.push_back(d_thr);
-    CTX_CUDA(cudaMalloc((void**)&d_blk, blk.size() * 8));
-    out->blk.push_back(d_blk);
-    // plain (synchronous) copies from pageable memory: complete before any kernel launched afterwards starts
-    CTX_CUDA(cudaMemcpy(d_thr, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice));
-    CTX_CUDA(cudaMemcpy(d_blk, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice));
-  }
-  CTX_CUDA(cudaDeviceSynchronize());  // the DMA of a pageable copy may trail its return; callers' streams need not be blocking
-  return NTT256_OK;
 }
 
 int get_plan(ntt64_ctx* ctx, int log_n, int batch, const Plan** out, const ntt64_ctx::PlanTables** tabs,
@@ -298,11 +245,9 @@ int get_plan(ntt64_ctx* ctx, int log_n, int batch, const Plan** out, const ntt64
     Plan plan;
     if (!plan_for(log_n, key.tile_bits, key.group_bits, key.coalesce, ctx->max_log_n, &plan, fk)) return NTT256_ERR_PLAN;
     ntt64_ctx::PlanTables pt;
-    int rc = build_pass_tables(ctx, plan, &pt);
-    if (rc) {
-      for (u32* p : pt.thr) cudaFree(p);
-      for (uint2* p : pt.blk) cudaFree(p);
-      return rc;
+    if (ntt256::build_pass_tables(plan, &pt) != cudaSuccess) {
+      ctx->last_err = "index tables of a plan (cudaMalloc / cudaMemcpy)";
+      return NTT256_ERR_CUDA;
     }
     ctx->plan_tables.emplace(key, pt);
     it = ctx->plans.emplace(key, plan).first;

@@ -78,6 +78,11 @@ struct PassArgsT {
   unsigned long long sync_timeout_ns;
   unsigned int* sync_counter;         // CTA arrival counter of this context (device memory, zero between uses)
   int sync_mode, sync_nranks, sync_rank;
+  // Index tables of this pass, built on the host with the plan (pass_tables.h): per thread and round the local element
+  // index and its swizzled shared-memory offset, the global offsets of the thread's first element when loading /
+  // storing, its share of j_low; per CTA the tile base and its share of j_low.
+  const u32* thr;
+  const uint2* blk;
 };
 
 constexpr int kSyncSlotBase = 256 / 8;  // epochs start at byte 256 of a flag buffer (u64 slots, one per source rank)
@@ -162,11 +167,11 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename
   const u32 tile_words = 1u << T;
 
   // ---- block-level index pieces (uniform)
-  const unsigned long long blk = blockIdx.x;
-  const unsigned long long base_t = deposit64(blk, pd.blk_pos, pd.nblk_bits);  // index inside one transform
+  const uint2 bt = __ldg(A.blk + blockIdx.x);
+  const unsigned long long base_t = bt.x;  // index inside one transform
   unsigned long long base = base_t;
-  u32 jlow_blk = pd.jlow_const;
-  for (int i = 0; i < pd.nblk_bits; ++i) jlow_blk += (u32)((blk >> i) & 1ull) * pd.wt_blk[i];
+  const u32 jlow_blk = bt.y;
+  const u32 nthr = blockDim.x;
   base += (unsigned long long)blockIdx.y * A.batch_stride;
   const uint4* gbase_in = data_in + Q * base;
   uint4* gbase = data_out + Q * base;
@@ -197,7 +202,13 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename
   for (int r = gen ? pd.nrounds - 1 : 0; r < pd.nrounds; ++r) {
     const int sb = pd.round_sb[r];
     const int nb = pd.round_nb[r];
-    const u32 lam0 = deposit32(tid, pd.tmap[r], T - GB);
+    const u32 lw = __ldg(A.thr + (3 + r) * nthr + tid);
+    const u32 lam0 = lw & 0xffffu;
+    const u32 w0 = lw >> 16;  // swz(lam0)
+    // swz is linear over XOR: the swizzled offset of element u is w0 ^ (XOR of sx[i] over the set bits i of u)
+    u32 sx[GB];
+#pragma unroll
+    for (int i = 0; i < GB; ++i) sx[i] = swz(1u << (sb + i));
     const bool first = (r == 0);
     const bool last = (r == pd.nrounds - 1);
 
@@ -208,7 +219,7 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename
 #pragma unroll
         for (int k = 0; k < NL; ++k) x[u][k] = A.one[k];
     } else if (first) {
-      const u32 g0 = deposit32(lam0, pd.in_pos, T);
+      const u32 g0 = __ldg(A.thr + tid);
       u32 st[GB];
 #pragma unroll
       for (int i = 0; i < GB; ++i) st[i] = 1u << pd.in_pos[sb + i];
@@ -225,10 +236,11 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename
         }
       }
     } else {
-      const u32 w0 = swz(lam0);
 #pragma unroll
       for (int u = 0; u < NE; ++u) {
-        const u32 w = w0 ^ swz((u32)u << sb);
+        u32 w = w0;
+#pragma unroll
+        for (int i = 0; i < GB; ++i) w ^= ((u >> i) & 1) ? sx[i] : 0u;
 #pragma unroll
         for (int k = 0; k < NL; ++k) x[u][k] = smem[k * tile_words + w];
       }
@@ -251,17 +263,18 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename
 
     if (!last) {
       // ---- exchange
-      const u32 w0 = swz(lam0);
 #pragma unroll
       for (int u = 0; u < NE; ++u) {
-        const u32 w = w0 ^ swz((u32)u << sb);
+        u32 w = w0;
+#pragma unroll
+        for (int i = 0; i < GB; ++i) w ^= ((u >> i) & 1) ? sx[i] : 0u;
 #pragma unroll
         for (int k = 0; k < NL; ++k) smem[k * tile_words + w] = x[u][k];
       }
       __syncthreads();
     } else {
       // ---- pass twiddle, scale, canonical form, store
-      const u32 g0 = deposit32(lam0, pd.out_pos, T);
+      const u32 g0 = __ldg(A.thr + nthr + tid);
       u32 st[GB];
 #pragma unroll
       for (int i = 0; i < GB; ++i) st[i] = 1u << pd.out_pos[sb + i];
@@ -276,8 +289,7 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename
           F::mul_tw(x[u], w, f);
         }
       } else if (pd.has_tw) {
-        u32 jl0 = jlow_blk;
-        for (int i = 0; i < lowp; ++i) jl0 += ((lam0 >> i) & 1u) * pd.wt_loc[i];
+        const u32 jl0 = jlow_blk + __ldg(A.thr + 2 * nthr + tid);
         u32 gw[GB];
 #pragma unroll
         for (int i = 0; i < GB; ++i) gw[i] = (sb + i < lowp) ? pd.wt_loc[sb + i] : 0u;
