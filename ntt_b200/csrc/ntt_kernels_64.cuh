@@ -91,6 +91,14 @@ NTT_DEV void round_compute64(u64* x, const PassArgs64& A, bool last, bool scaled
   const u32 tl0 = (lam0 >> lowp) & tl_mask;
   const int ush = sb - lowp;
   const u64* loc_tab = scaled ? A.loc_scaled : A.loc;
+  const u32 loc_mask = (1u << A.loc_bits) - 1u;
+  // shift and sign of the table index once per round (on tau_lo): one constant multiply and one mask per element
+  u32 tbase[1 << (GB - NB)];
+#pragma unroll
+  for (int rst = 0; rst < (1 << (GB - NB)); ++rst) {
+    const u32 t0 = ((tl0 | ((u32)rst << ush)) & tl_mask) << sh;
+    tbase[rst] = A.inverse ? (0u - t0) : t0;
+  }
 #pragma unroll
   for (int u = 0; u < (1 << GB); ++u) {
     const int uproc = u >> (GB - NB);
@@ -99,10 +107,7 @@ NTT_DEV void round_compute64(u64* x, const PassArgs64& A, bool last, bool scaled
     for (int i = 0; i < NB; ++i) v |= ((uproc >> i) & 1) << (NB - 1 - i);
     const u32 rest = u & ((1 << (GB - NB)) - 1);
     if (scaled || uproc != 0) {
-      const u32 tl = (tl0 | (rest << ush)) & tl_mask;
-      u32 e = (tl * (u32)v) << sh;
-      if (A.inverse) e = (0u - e);
-      e &= (1u << A.loc_bits) - 1u;
+      const u32 e = (tbase[rest] * (u32)v) & loc_mask;
       x[u] = F::mul(__ldg(loc_tab + e), x[u], f);
     }
   }

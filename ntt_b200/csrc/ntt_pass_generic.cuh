@@ -122,6 +122,15 @@ NTT_DEV void round_compute(u32 (*x)[F::NL], const typename F::Args& A, const typ
   const u32 tl0 = (lam0 >> lowp) & tl_mask;
   const int ush = sb - lowp;    // >= 0 here (only the last round can dip below)
   const uint4* loc_tab = scaled ? A.loc_scaled : A.loc;
+  const u32 loc_mask = (1u << A.loc_bits) - 1u;
+  // the table index of element u is (tau_lo * v_u) << sh, negated for the inverse: the shift and the sign are taken
+  // once per round (on tau_lo), which leaves one multiply by the constant v_u and one mask per element
+  u32 tbase[1 << (GB - NB)];
+#pragma unroll
+  for (int rst = 0; rst < (1 << (GB - NB)); ++rst) {
+    const u32 t0 = ((tl0 | ((u32)rst << ush)) & tl_mask) << sh;
+    tbase[rst] = A.inverse ? (0u - t0) : t0;
+  }
 #pragma unroll
   for (int u = 0; u < (1 << GB); ++u) {
     // v = bit-reversed processed bits of u; tau_lo includes the group's unprocessed bits
@@ -131,10 +140,7 @@ NTT_DEV void round_compute(u32 (*x)[F::NL], const typename F::Args& A, const typ
     for (int i = 0; i < NB; ++i) v |= ((uproc >> i) & 1) << (NB - 1 - i);
     const u32 rest = u & ((1 << (GB - NB)) - 1);
     if (scaled || uproc != 0) {
-      const u32 tl = (tl0 | (rest << ush)) & tl_mask;
-      u32 e = (tl * (u32)v) << sh;
-      if (A.inverse) e = (0u - e);
-      e &= (1u << A.loc_bits) - 1u;
+      const u32 e = (tbase[rest] * (u32)v) & loc_mask;
       u32 w[F::TW];
       F::ld_tw(w, loc_tab, e);
       F::mul_tw(x[u], w, f);
@@ -296,10 +302,17 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename
         const u32 nmask = (A.hi_bits + A.lo_bits >= 32) ? 0xffffffffu : ((1u << (A.hi_bits + A.lo_bits)) - 1u);
         const u32 lomask = (1u << A.lo_bits) - 1u;
         const bool two = pd.tw_lshift < A.lo_bits;
+        // k_hi = the bit-reversed processed bits of the element's local index: the thread's part once, the
+        // element's part as an OR of per-bit constants (disjoint bits)
+        const u32 khi0 = d ? (__brev(lam0 >> lowp) >> (32 - d)) : 0u;
+        u32 kb[GB];
+#pragma unroll
+        for (int i = 0; i < GB; ++i) kb[i] = d ? (__brev((1u << (sb + i)) >> lowp) >> (32 - d)) : 0u;
 #pragma unroll
         for (int u = 0; u < NE; ++u) {
-          const u32 lam = lam0 | ((u32)u << sb);
-          const u32 khi = d ? (__brev(lam >> lowp) >> (32 - d)) : 0u;
+          u32 khi = khi0;
+#pragma unroll
+          for (int i = 0; i < GB; ++i) khi |= ((u >> i) & 1) ? kb[i] : 0u;
           u32 jl = jl0;
 #pragma unroll
           for (int i = 0; i < GB; ++i) jl += ((u >> i) & 1) ? gw[i] : 0u;
