@@ -244,8 +244,12 @@ def emit_cuda() -> str:
             w(f"  fn::{fnname}({d}, {_operand(a)}, {_operand(b)});")
     w("  // step 3: r in [0, 3p) -> [0, 2p + 2^192): subtract p (add 2^256 - p) when the top 64 bits of r exceed those")
     w("  // of 2p -- then r >= 2p for certain; otherwise r < 2p + 2^192 (the wide-lazy range of field_wl.cuh)")
+    w("  // The quotient estimate is one short at most except in a sliver of cases, so r < 2p for nearly every lane:")
+    w("  // a warp in which no lane needs the correction skips its ten instructions (predicated-off instructions")
+    w("  // still take issue slots, and issue slots are what this product is short of).")
     args_out = ", ".join(f'"+r"({outs[k]})' for k in range(8))
     args_in = ", ".join(f'"r"(f.pbar[{k}])' for k in range(8))
+    w(f"  if (__any_sync(__activemask(), (((unsigned long long){outs[7]} << 32) | {outs[6]}) > (((unsigned long long)f.p2[7] << 32) | f.p2[6])))")
     w('  asm volatile("{\\n\\t.reg .pred q;\\n\\t.reg .u64 a, b;\\n\\t"')
     w('      "mov.b64 a, {%6, %7};\\n\\t"')
     w('      "mov.b64 b, {%16, %17};\\n\\t"')
