@@ -88,6 +88,9 @@ size_t ntt256_ctx_table_bytes(const ntt256_ctx* ctx, size_t* streamed_bytes);
  * becomes resident and does its index arithmetic while pass i drains its last wave, and touches no data before
  * pass i has completed.  enable = 0 restores plain stream-ordered launches (same results). */
 int ntt256_ctx_set_dependent_launch(ntt256_ctx* ctx, int enable);
+/* BN254 Fr contexts run the throughput kernel in an instance whose field constants are compile-time immediates
+ * (default on; same bits).  enable = 0 keeps them on the generic instance (testing). */
+int ntt256_ctx_set_constant_field_kernel(ntt256_ctx* ctx, int enable);
 /* Calls with batch * 2^log_n <= max_elements (default 2^17) are latency-bound and run on the
  * four-elements-per-thread kernel, those of at most half that on the two-elements-per-thread
  * kernel (more, shorter threads); 0 keeps every call on the throughput kernel. */

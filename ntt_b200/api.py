@@ -112,6 +112,10 @@ class Ntt256:
         """Programmatic dependent launch between the pass kernels (default on)."""
         self._check(self._L.ntt256_ctx_set_dependent_launch(self._h, int(bool(enable))))
 
+    def set_constant_field_kernel(self, enable: bool):
+        """BN254 Fr: throughput kernel with compile-time field constants (default on) or the generic instance."""
+        self._check(self._L.ntt256_ctx_set_constant_field_kernel(self._h, int(bool(enable))))
+
     def set_twiddle_mode(self, shoup: bool):
         """True: (w, floor(w 2^256/p)) tables and Shoup products (fields with p < 2^254); False: Montgomery."""
         self._check(self._L.ntt256_ctx_set_twiddle_mode(self._h, int(bool(shoup))))

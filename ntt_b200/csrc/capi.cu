@@ -75,6 +75,8 @@ struct ntt256_ctx {
   // programmatic dependent launch between the pass kernels of a stream (a pass becomes resident, and computes its
   // indices, while its predecessor drains its last wave)
   bool use_pdl = true;
+  bool const_field = false;      // the modulus is BN254 Fr: the throughput kernel with compile-time field constants applies
+  bool use_const_field = true;   // testing knob
   std::map<int, uint4*> loc_scaled;       // log_n -> (1/n) * loc[] : folds the inverse scaling into a round twiddle
   // streamed pass-twiddle arrays, keyed by (plan id, pass index, direction)
   struct TwStream {
@@ -264,9 +266,14 @@ struct FuseSpec {  // element-wise companions fused into the first / last pass (
 };
 
 // The pass kernel for 2^group_bits elements per thread; FZ instances only for launches that carry companions.
+// const_field: the context's modulus is the one ntt_pass_bn254_kernel is compiled for
 void launch_pass(bool shoup, int group_bits, bool dense, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream,
-                 const uint4* in, uint4* out, const PassArgs& A, bool pdl) {
+                 const uint4* in, uint4* out, const PassArgs& A, bool pdl, bool const_field = false) {
   const bool fz = A.in_scale || A.out_scale || A.out_mul;
+  if (shoup && const_field && !fz && group_bits == 3) {
+    launch_pass_bn254(grid, threads, smem, stream, in, out, A, pdl);
+    return;
+  }
   if (shoup) {
     if (fz) launch_pass_inst<true, true>(group_bits, dense, grid, threads, smem, stream, in, out, A, pdl);
     else launch_pass_inst<true, false>(group_bits, dense, grid, threads, smem, stream, in, out, A, pdl);
@@ -376,7 +383,7 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
             const int Tg = G.pd.T;
             dim3 ggrid((unsigned)(1ull << G.pd.nblk_bits), 1, 1);
             launch_pass(sh, plan.group_bits, ctx->dense_pass4, ggrid, 1u << (Tg - plan.group_bits), (size_t)32 << Tg, stream,
-                        (const uint4*)d_data, (uint4*)d_data, G, false);
+                        (const uint4*)d_data, (uint4*)d_data, G, false, ctx->const_field && ctx->use_const_field);
             ++ctx->launches;
             CTX_CUDA(cudaGetLastError());
             // one-off: the array may be read from other streams by later calls
@@ -428,7 +435,8 @@ int run_plan(ntt256_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
     // first pass may read from `src_first`, last pass may write to `dst_last` (host-mapped buffers)
     const uint4* pin = (i == 0 && io && io->src_first) ? (const uint4*)io->src_first : (const uint4*)d_data;
     uint4* pout = (i + 1 == plan.passes.size() && io && io->dst_last) ? (uint4*)io->dst_last : (uint4*)d_data;
-    launch_pass(sh, GB, ctx->dense_pass4, grid, threads, smem, stream, pin, pout, A, ctx->use_pdl);
+    launch_pass(sh, GB, ctx->dense_pass4, grid, threads, smem, stream, pin, pout, A, ctx->use_pdl,
+                ctx->const_field && ctx->use_const_field);
     ++ctx->launches;
     CTX_CUDA(cudaGetLastError());
   }
@@ -801,6 +809,8 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
       ctx->tw_stream_budget = total_b / 5;
     }
   }
+  ctx->const_field = pass_bn254_params_match(ctx->fp);
+  if (!pass_bn254_set_smem(32 << kMaxTileBits)) return fail(NTT256_ERR_CUDA);
   const int big = 32 << kMaxTileBits, small = 32 << 11;
   if (!pass_inst_set_smem<false, false>(big, small) || !pass_inst_set_smem<false, true>(big, small) ||
       !pass_inst_set_smem<true, false>(big, small) || !pass_inst_set_smem<true, true>(big, small))
@@ -1301,6 +1311,12 @@ int ntt256_ctx_set_elements_per_thread(ntt256_ctx* ctx, int log2_elements) {
 int ntt256_ctx_set_dependent_launch(ntt256_ctx* ctx, int enable) {
   if (!ctx) return NTT256_ERR_ARG;
   ctx->use_pdl = enable != 0;
+  return NTT256_OK;
+}
+
+int ntt256_ctx_set_constant_field_kernel(ntt256_ctx* ctx, int enable) {
+  if (!ctx) return NTT256_ERR_ARG;
+  ctx->use_const_field = enable != 0;
   return NTT256_OK;
 }
 

@@ -159,6 +159,7 @@ struct F256 {
   static constexpr int TW = SH ? 16 : 8;
   using Params = FieldParams;
   using Args = PassArgs;
+  static NTT_DEV const FieldParams& params(const Args& A) { return A.f; }
   static NTT_DEV void ld(u32* v, const uint4* p) { ld_global_256(v, p); }
   static NTT_DEV void st(uint4* p, const u32* v) { st_global_256(p, v); }
   static NTT_DEV void ld_tw(u32* w, const uint4* tab, u32 idx) { ld_tw_256<SH>(w, w + 8, tab, idx); }

@@ -64,6 +64,7 @@ struct FN {
   static constexpr int TW = NLIMBS;
   using Params = FieldParamsN<NLIMBS>;
   using Args = PassArgsT<Params, NLIMBS, NLIMBS>;
+  static NTT_DEV const Params& params(const Args& A) { return A.f; }
   static NTT_DEV void ld(u32* v, const uint4* p) { ld_el<NL>(v, p); }
   static NTT_DEV void st(uint4* p, const u32* v) { st_el<NL>(p, v); }
   static NTT_DEV void ld_tw(u32* w, const uint4* tab, u32 idx) { ld_table_n<NL>(w, tab, idx); }

@@ -4,7 +4,8 @@
 //
 //   F::NL        u32 limbs per element (8: 256-bit containers, 12: 384-bit ...)
 //   F::TW        u32 words per twiddle-table entry (NL for Montgomery tables, 2 NL for Shoup pairs)
-//   F::Args      the PassArgsT instance the kernels take by value
+//   F::Args      the PassArgsT instance the kernels take by value;   F::params(A)   the field constants (A.f, or
+//                compile-time constants for an instance specialised on one modulus)
 //   F::ld / st   one element from / to global memory
 //   F::ld_tw     table entry idx -> TW words;   F::mul_tw   x <- w * x
 //   F::bfly      (a, b) <- (a + b, a - b) under the policy's lazy ranges (to_mul: the difference meets a product next)
@@ -166,7 +167,7 @@ NTT_DEV void ntt_pass_body(const uint4* data_in, uint4* data_out, const typename
   constexpr int NL = F::NL;
   constexpr int Q = NL / 4;  // uint4 per element
   const PassDesc& pd = A.pd;
-  const typename F::Params& f = A.f;
+  const typename F::Params& f = F::params(A);
   const int T = pd.T;
   const int d = pd.d;
   const u32 tid = threadIdx.x;

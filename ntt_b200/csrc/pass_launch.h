@@ -13,6 +13,12 @@ using PassArgs = PassArgsT<FieldParams, 8, 16>;
 template <bool SH, bool FZ>
 void launch_pass_inst(int group_bits, bool dense, dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const uint4* in,
                       uint4* out, const PassArgs& A, bool pdl);
+// The eight-elements-per-thread Shoup kernel specialised on BN254 Fr (constants as immediates; plain launches only);
+// pass_bn254_params_match: the context's constants are exactly the compiled-in ones.
+void launch_pass_bn254(dim3 grid, unsigned threads, size_t smem, cudaStream_t stream, const uint4* in, uint4* out, const PassArgs& A,
+                       bool pdl);
+bool pass_bn254_set_smem(int bytes);
+bool pass_bn254_params_match(const FieldParams& f);
 // dense: four elements per thread on the three-CTAs-per-SM instance (ntt_pass4h_kernel) when the CTA fits it
 // raises the dynamic shared memory limit of the three kernels of one instance; false on a CUDA error
 template <bool SH, bool FZ>

@@ -16,7 +16,7 @@ FIELD_BN254_FR, FIELD_BLS12_381_FR = 0, 1
 # every symbol include/ntt256.h declares
 EXPORTS = [
     "ntt256_ctx_create", "ntt256_ctx_create_named", "ntt256_ctx_destroy", "ntt256_ctx_set_tuning",
-    "ntt256_ctx_set_stream_twiddle_limit", "ntt256_ctx_set_stream_twiddle_budget", "ntt256_ctx_table_bytes", "ntt256_ctx_set_small_transform_limit", "ntt256_ctx_set_dependent_launch", "ntt256_ctx_set_elements_per_thread",
+    "ntt256_ctx_set_stream_twiddle_limit", "ntt256_ctx_set_stream_twiddle_budget", "ntt256_ctx_table_bytes", "ntt256_ctx_set_small_transform_limit", "ntt256_ctx_set_constant_field_kernel", "ntt256_ctx_set_dependent_launch", "ntt256_ctx_set_elements_per_thread",
     "ntt256_ctx_set_twiddle_mode", "ntt256_ctx_get_twiddle_mode",
     "ntt256_forward", "ntt256_inverse", "ntt256_forward_batch", "ntt256_inverse_batch",
     "ntt256_forward_host", "ntt256_inverse_host", "ntt256_fourstep_step1", "ntt256_fourstep_step2", "ntt256_fourstep_step1_peer", "ntt256_enable_peer_access",
@@ -79,6 +79,7 @@ def lib() -> ctypes.CDLL:
         L.ntt256_ctx_table_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
         L.ntt256_ctx_table_bytes.restype = ctypes.c_size_t
         L.ntt256_ctx_set_small_transform_limit.argtypes = [vp, ctypes.c_longlong]
+        L.ntt256_ctx_set_constant_field_kernel.argtypes = [vp, ci]
         L.ntt256_ctx_set_dependent_launch.argtypes = [vp, ci]
         L.ntt256_ctx_set_elements_per_thread.argtypes = [vp, ci]
         L.ntt256_ctx_set_twiddle_mode.argtypes = [vp, ci]

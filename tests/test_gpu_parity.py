@@ -709,6 +709,42 @@ def test_dependent_launch_on_and_off_give_the_same_bits(torch_cuda):
     ctx.close()
 
 
+def test_constant_field_kernel_matches_the_generic_instance(torch_cuda):
+    """BN254 Fr contexts run the throughput kernel in an instance whose field constants are compile-time immediates:
+    same bits as the generic instance and the oracle (forward, inverse, batches, a four-step shard), and a context
+    over another modulus never selects it."""
+    from ntt_b200 import dist as nd
+    from ntt_b200.api import FIELDS, Ntt256
+    from oracle import c_oracle as co
+
+    torch = torch_cuda
+    p, g = FIELDS["bn254_fr"]
+    ctx = Ntt256("bn254_fr", max_log_n=22)
+    for log_n, batch in ((21, 1), (22, 1), (16, 20), (12, 300)):
+        x = co.splitmix_elements(batch << log_n, p, 901 + log_n)
+        want = co.ntt(x[: 1 << log_n], p, g, threads=8)
+        outs = []
+        for enable in (True, False):
+            ctx.set_constant_field_kernel(enable)
+            got = _gpu_forward(torch, ctx, x, log_n, batch)
+            assert np.array_equal(got[: 1 << log_n], want), (log_n, batch, enable)
+            assert np.array_equal(_gpu_forward(torch, ctx, got, log_n, batch, inverse=True), x), (log_n, batch, enable)
+            outs.append(got)
+        assert np.array_equal(outs[0], outs[1])
+    log_n, lr, lp = 22, nd.default_log_r(22), 2
+    sh = co.splitmix_elements(1 << (log_n - lp), p, 77)
+    outs = []
+    for enable in (True, False):
+        ctx.set_constant_field_kernel(enable)
+        d = torch.from_numpy(sh.view(np.int32).copy()).cuda().view(-1)
+        ctx.fourstep_step1(d, log_n, lr, lp, 3)
+        ctx.fourstep_step2(d, log_n, lr, lp, 3)
+        torch.cuda.synchronize()
+        outs.append(d.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    ctx.close()
+
+
 def test_zero_copy_host_buffers(torch_cuda, ctxs):
     """Pinned host buffers: the first pass reads host memory and the last pass writes it directly
     (no staging copies).  Distinct and aliased in/out buffers, one pass and several passes."""
