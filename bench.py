@@ -501,8 +501,8 @@ def _other_widths(torch, local_rank, steps):
         "value": n / ms * 1e3, "unit": UNIT, "G_butterflies_s": n / 2 * log_n / ms / 1e6, "passes_per_step": passes,
         "roofline_hbm": {"achieved": 16.0 * n * passes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
                          "frac": 16.0 * n * passes / ms / 1e6 / hbm_peak, "bytes": "16 B per element per pass"},
-        "bound": "integer ALU issue (add/sub/reduce of 64-bit residues on 32-bit lanes: ~42 instructions per "
-                 "butterfly, ALU pipe 60-72 % busy, HBM 13-39 % per pass: profiles/r02_ncu_summary_64.json)",
+        "bound": "integer ALU issue (add/sub/reduce of 64-bit residues on 32-bit lanes: ~36 instructions per "
+                 "butterfly, ALU pipe 64-72 % busy, HBM 17-47 % per pass: profiles/r02_ncu_summary_64.json)",
         "checked": "X[0] == sum x mod p"}
     c64.close()
     del d
@@ -692,7 +692,7 @@ def run_ours(args):
     hbm_achieved = alg_bytes_launch / (launch_ms / 1e3) / 1e9
     traffic, traffic_src = None, None
     if world == 1 and LOG_N == 24:
-        for name in ("r02_ncu_summary.json", "r01_ncu_summary.json"):
+        for name in ("r02_ncu_summary_final.json", "r02_ncu_summary.json", "r01_ncu_summary.json"):
             tpath = os.path.join(ROOT, "profiles", name)
             if os.path.exists(tpath):
                 try:

@@ -803,8 +803,8 @@ int ntt256_ctx_create(ntt256_ctx** out, int device, const uint32_t p[8], const u
     // a streamed first-pass twiddle array is as large as the transform itself (twice with Shoup pairs)
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) {
-      // one array may take a tenth of the device (2^28 points as Shoup pairs = 16 GiB on a 180 GB B200: 62.7 ms
-      // instead of 67.2 ms with two lookups, profiles/r02_large_1gpu.jsonl), all of them together a fifth
+      // one array may take a tenth of the device (2^28 points as Shoup pairs = 16 GiB on a 180 GB B200: 58.0 ms
+      // instead of 62.7 ms with two lookups, profiles/r02_large_1gpu.jsonl), all of them together a fifth
       ctx->tw_stream_limit = total_b / 10;
       ctx->tw_stream_budget = total_b / 5;
     }
