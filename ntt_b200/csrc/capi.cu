@@ -17,6 +17,7 @@
 #include "hostfield.h"
 #include "aux_kernels.cuh"
 #include "pass_launch.h"
+#include "host_common.h"
 #include "pass_tables.h"
 #include "plan.h"
 
@@ -250,20 +251,6 @@ int get_plan(ntt256_ctx* ctx, const PlanKey& key, const Plan** out) {
   *out = &it->second;
   return NTT256_OK;
 }
-
-struct PeerSpec {
-  const void* const* ptrs = nullptr;
-  int bits = 0, shift = 0, rank = 0;
-};
-struct IoSpec {  // optional out-of-place ends of a plan (device-visible pointers)
-  const void* src_first = nullptr;
-  void* dst_last = nullptr;
-};
-struct FuseSpec {  // element-wise companions fused into the first / last pass (PassArgs::in_scale ...)
-  const uint4* in_scale = nullptr;
-  const uint4* out_scale = nullptr;
-  const uint4* out_mul = nullptr;
-};
 
 // The pass kernel for 2^group_bits elements per thread; FZ instances only for launches that carry companions.
 // const_field: the context's modulus is the one ntt_pass_bn254_kernel is compiled for
@@ -576,39 +563,10 @@ int transform_host(ntt256_ctx* ctx, const void* h_in, void* h_out, int log_n, in
     CTX_CUDA(cudaStreamSynchronize(0));
     return NTT256_OK;
   }
-  if (!ctx->s_h2d) {
-    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
-    for (int i = 0; i < 3; ++i) {
-      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
-      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
-      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
-    }
-  }
-  const size_t slot_bytes = one * per_chunk;
-  int rc = ensure_stage(ctx, 3 * slot_bytes);
+  int rc = ensure_stage(ctx, 3 * one * per_chunk);
   if (rc) return rc;
-  cudaStream_t s_comp = ctx->s_comp;
-  const int nchunks = (batch + per_chunk - 1) / per_chunk;
-  for (int c = 0; c < nchunks; ++c) {
-    const int slot = c % 3;
-    const int b0 = c * per_chunk, nb = std::min(per_chunk, batch - b0);
-    char* d = (char*)ctx->d_stage + slot * slot_bytes;
-    if (c >= 3) CTX_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_out[slot], 0));  // slot drained
-    CTX_CUDA(cudaMemcpyAsync(d, (const char*)h_in + (size_t)b0 * one, (size_t)nb * one, cudaMemcpyHostToDevice, ctx->s_h2d));
-    CTX_CUDA(cudaEventRecord(ctx->ev_in[slot], ctx->s_h2d));
-    CTX_CUDA(cudaStreamWaitEvent(s_comp, ctx->ev_in[slot], 0));
-    rc = transform(ctx, d, log_n, nb, inverse, s_comp);
-    if (rc) return rc;
-    CTX_CUDA(cudaEventRecord(ctx->ev_done[slot], s_comp));
-    CTX_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[slot], 0));
-    CTX_CUDA(cudaMemcpyAsync((char*)h_out + (size_t)b0 * one, d, (size_t)nb * one, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    CTX_CUDA(cudaEventRecord(ctx->ev_out[slot], ctx->s_d2h));
-  }
-  CTX_CUDA(cudaStreamSynchronize(ctx->s_d2h));
-  CTX_CUDA(cudaStreamSynchronize(s_comp));
-  return NTT256_OK;
+  return host_ring(ctx, h_in, h_out, one, batch, per_chunk,
+                   [&](void* d, int nb, cudaStream_t s) { return transform(ctx, d, log_n, nb, inverse, s); });
 }
 
 // Multiplied-out shift^j tables trade 32 B/element of memory and HBM traffic for one of the two
@@ -1265,27 +1223,7 @@ size_t ntt256_ctx_table_bytes(const ntt256_ctx* ctx, size_t* streamed_bytes) {
 }
 
 int ntt256_ctx_set_peer_sync(ntt256_ctx* ctx, void* const* flag_bufs, int nranks, int rank, double timeout_s) {
-  if (!ctx) return NTT256_ERR_ARG;
-  CTX_CUDA(cudaSetDevice(ctx->device));
-  if (!flag_bufs || nranks <= 1) {  // disarm
-    ctx->sync_nranks = 0;
-    ctx->sync_epoch = 0;
-    return NTT256_OK;
-  }
-  if (nranks > 8 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return NTT256_ERR_ARG;
-  for (int r = 0; r < nranks; ++r) {
-    if (!flag_bufs[r]) return NTT256_ERR_ARG;
-    ctx->sync_flags[r] = (unsigned long long)flag_bufs[r];
-  }
-  if (!ctx->sync_counter) {
-    CTX_CUDA(cudaMalloc((void**)&ctx->sync_counter, sizeof(unsigned int)));
-    CTX_CUDA(cudaMemset(ctx->sync_counter, 0, sizeof(unsigned int)));
-  }
-  ctx->sync_nranks = nranks;
-  ctx->sync_rank = rank;
-  ctx->sync_epoch = 0;
-  if (timeout_s > 0) ctx->sync_timeout_ns = (unsigned long long)(timeout_s * 1e9);
-  return NTT256_OK;
+  return set_peer_sync_impl(ctx, flag_bufs, nranks, rank, timeout_s);
 }
 
 int ntt256_ctx_set_twiddle_mode(ntt256_ctx* ctx, int shoup) {

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/ntt384.h"
+#include "host_common.h"
 #include "hostfield_n.h"
 #include "ntt_kernels_n.cuh"
 #include "pass_tables.h"
@@ -146,20 +147,6 @@ const U384& inv_pow2(ntt384_ctx* ctx, int k) {
   }
   return ctx->ninv[k];
 }
-
-struct PeerSpec {
-  const void* const* ptrs = nullptr;
-  int bits = 0, shift = 0, rank = 0;
-};
-struct IoSpec {  // optional out-of-place ends of a plan (device-visible pointers)
-  const void* src_first = nullptr;
-  void* dst_last = nullptr;
-};
-struct FuseSpec {  // element-wise companions fused into the first / last pass (PassArgsT::in_scale ...)
-  const uint4* in_scale = nullptr;
-  const uint4* out_scale = nullptr;
-  const uint4* out_mul = nullptr;
-};
 
 // sync: bit 0 the first pass waits for every rank's epoch; bit 1 the last pass publishes this rank's epoch
 int run_plan(ntt384_ctx* ctx, const Plan& plan, void* d_data, unsigned long long batch_stride, int batch, bool inverse,
@@ -579,27 +566,7 @@ int ntt384_fourstep_inverse_step2(ntt384_ctx* ctx, void* d_shard, int log_n, int
 }
 
 int ntt384_ctx_set_peer_sync(ntt384_ctx* ctx, void* const* flag_bufs, int nranks, int rank, double timeout_s) {
-  if (!ctx) return NTT256_ERR_ARG;
-  CTX_CUDA(cudaSetDevice(ctx->device));
-  if (!flag_bufs || nranks <= 1) {  // disarm
-    ctx->sync_nranks = 0;
-    ctx->sync_epoch = 0;
-    return NTT256_OK;
-  }
-  if (nranks > 8 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return NTT256_ERR_ARG;
-  for (int r = 0; r < nranks; ++r) {
-    if (!flag_bufs[r]) return NTT256_ERR_ARG;
-    ctx->sync_flags[r] = (unsigned long long)flag_bufs[r];
-  }
-  if (!ctx->sync_counter) {
-    CTX_CUDA(cudaMalloc((void**)&ctx->sync_counter, sizeof(unsigned int)));
-    CTX_CUDA(cudaMemset(ctx->sync_counter, 0, sizeof(unsigned int)));
-  }
-  ctx->sync_nranks = nranks;
-  ctx->sync_rank = rank;
-  ctx->sync_epoch = 0;
-  if (timeout_s > 0) ctx->sync_timeout_ns = (unsigned long long)(timeout_s * 1e9);
-  return NTT256_OK;
+  return set_peer_sync_impl(ctx, flag_bufs, nranks, rank, timeout_s);
 }
 
 int ntt384_vec_mul(ntt384_ctx* ctx, void* d_out, const void* d_a, const void* d_b, unsigned long long n, int mont_form,

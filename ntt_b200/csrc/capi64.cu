@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/ntt64.h"
+#include "host_common.h"
 #include "ntt_kernels_64.cuh"
 #include "pass_tables.h"
 #include "plan.h"
@@ -308,15 +309,10 @@ struct Fuse64 {
   bool out_has_ninv = false;  // out_scale already carries 1/n
 };
 
-struct Peer64 {
-  const void* const* ptrs = nullptr;
-  int bits = 0, shift = 0, rank = 0;
-};
-
 // The passes of one plan over `batch` transforms starting at `p` (batch <= 65535); scale_log_n >= 0: multiply by
 // 2^-scale_log_n on the way (folded into a round-twiddle table when the last pass has two rounds).
 int run_plan64(ntt64_ctx* ctx, const Plan& plan, const ntt64_ctx::PlanTables& tabs, u64* p, unsigned long long batch_stride,
-               int batch, bool inverse, int scale_log_n, cudaStream_t stream, const Fuse64* fuse, const Peer64* peer) {
+               int batch, bool inverse, int scale_log_n, cudaStream_t stream, const Fuse64* fuse, const ntt256::PeerSpec* peer) {
   PassArgs64 A;
   std::memset(&A, 0, sizeof(A));
   A.f = ctx->fp;
@@ -443,7 +439,7 @@ int fourstep64(ntt64_ctx* ctx, int kind, void* d_shard, int log_n, int log_r, in
   const ntt64_ctx::PlanTables* tabs = nullptr;
   int rc = get_plan(ctx, log_n, 1, &plan, &tabs, &fk);
   if (rc) return rc;
-  Peer64 ps;
+  ntt256::PeerSpec ps;
   if (peer_recv && log_p > 0) {
     if (log_p > 3) return NTT256_ERR_ARG;
     ps.ptrs = peer_recv;
@@ -486,38 +482,10 @@ int transform_host(ntt64_ctx* ctx, const void* h_in, void* h_out, int log_n, int
     CTX_CUDA(cudaStreamSynchronize(0));
     return NTT256_OK;
   }
-  if (!ctx->s_h2d) {
-    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-    CTX_CUDA(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
-    for (int i = 0; i < 3; ++i) {
-      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
-      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
-      CTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
-    }
-  }
-  const size_t slot_bytes = one * per_chunk;
-  int rc = ensure_stage(ctx, 3 * slot_bytes);
+  int rc = ensure_stage(ctx, 3 * one * per_chunk);
   if (rc) return rc;
-  const int nchunks = (batch + per_chunk - 1) / per_chunk;
-  for (int c = 0; c < nchunks; ++c) {
-    const int slot = c % 3;
-    const int b0 = c * per_chunk, nb = std::min(per_chunk, batch - b0);
-    char* d = (char*)ctx->d_stage + slot * slot_bytes;
-    if (c >= 3) CTX_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_out[slot], 0));  // slot drained
-    CTX_CUDA(cudaMemcpyAsync(d, (const char*)h_in + (size_t)b0 * one, (size_t)nb * one, cudaMemcpyHostToDevice, ctx->s_h2d));
-    CTX_CUDA(cudaEventRecord(ctx->ev_in[slot], ctx->s_h2d));
-    CTX_CUDA(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_in[slot], 0));
-    rc = transform(ctx, d, log_n, nb, inverse, ctx->s_comp);
-    if (rc) return rc;
-    CTX_CUDA(cudaEventRecord(ctx->ev_done[slot], ctx->s_comp));
-    CTX_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[slot], 0));
-    CTX_CUDA(cudaMemcpyAsync((char*)h_out + (size_t)b0 * one, d, (size_t)nb * one, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    CTX_CUDA(cudaEventRecord(ctx->ev_out[slot], ctx->s_d2h));
-  }
-  CTX_CUDA(cudaStreamSynchronize(ctx->s_d2h));
-  CTX_CUDA(cudaStreamSynchronize(ctx->s_comp));
-  return NTT256_OK;
+  return ntt256::host_ring(ctx, h_in, h_out, one, batch, per_chunk,
+                   [&](void* d, int nb, cudaStream_t s) { return transform(ctx, d, log_n, nb, inverse, s); });
 }
 
 void free_coset(ntt64_ctx::Coset& c) {
