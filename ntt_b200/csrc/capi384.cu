@@ -233,8 +233,22 @@ int run_plan(ntt384_ctx* ctx, const Plan& plan, void* d_data, unsigned long long
     uint4* pout = (last_pass && io && io->dst_last) ? (uint4*)io->dst_last : (uint4*)d_data;
     const unsigned threads = 1u << (T - 2);
     const size_t smem = (size_t)(4 * NL) << T;
-    if (fz) ntt384_pass_kernel<true><<<grid, threads, smem, stream>>>(pin, pout, A);
-    else ntt384_pass_kernel<false><<<grid, threads, smem, stream>>>(pin, pout, A);
+    {
+      // programmatic stream serialization (see grid_dependency_wait in ntt_pass_generic.cuh): the pass becomes resident
+      // while its predecessor drains and waits before it touches data
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(threads, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (fz) cudaLaunchKernelEx(&cfg, ntt384_pass_kernel<true>, pin, (uint4*)pout, A);
+      else cudaLaunchKernelEx(&cfg, ntt384_pass_kernel<false>, pin, (uint4*)pout, A);
+    }
     ++ctx->launches;
     CTX_CUDA(cudaGetLastError());
   }
