@@ -40,34 +40,46 @@ inline uint32_t pass_tables_deposit(unsigned long long v, const int8_t* pos, int
 }
 inline uint32_t pass_tables_swz(uint32_t l) { return l ^ ((l >> 5) & 31u) ^ ((l >> 10) & 31u); }  // kernel_common.cuh swz
 
+// The tables of one pass, on the host (pure arithmetic: tests/cpp/pass_tables_test.cpp checks their invariants without a GPU).
+inline void compute_pass_tables(const PassDesc& pd, int GB, std::vector<uint32_t>* thr_out, std::vector<uint2>* blk_out) {
+  const int T = pd.T, lowp = pd.T - pd.d;
+  const uint32_t t = 1u << (T - GB);
+  std::vector<uint32_t>& thr = *thr_out;
+  thr.assign((size_t)(3 + pd.nrounds) * t, 0u);
+  for (uint32_t tid = 0; tid < t; ++tid) {
+    const uint32_t lam_first = pass_tables_deposit(tid, pd.tmap[0], T - GB);
+    const uint32_t lam_last = pass_tables_deposit(tid, pd.tmap[pd.nrounds - 1], T - GB);
+    thr[tid] = pass_tables_deposit(lam_first, pd.in_pos, T);
+    thr[t + tid] = pass_tables_deposit(lam_last, pd.out_pos, T);
+    uint32_t jl = 0;
+    for (int i = 0; i < lowp; ++i) jl += ((lam_last >> i) & 1u) * pd.wt_loc[i];
+    thr[2 * t + tid] = jl;
+    for (int r = 0; r < pd.nrounds; ++r) {
+      const uint32_t lam = pass_tables_deposit(tid, pd.tmap[r], T - GB);
+      thr[(size_t)(3 + r) * t + tid] = lam | (pass_tables_swz(lam) << 16);
+    }
+  }
+  const size_t nblk = (size_t)1 << pd.nblk_bits;
+  std::vector<uint2>& blk = *blk_out;
+  blk.resize(nblk);
+  for (size_t b = 0; b < nblk; ++b) {
+    uint32_t jl = pd.jlow_const;
+    for (int i = 0; i < pd.nblk_bits; ++i) jl += (uint32_t)((b >> i) & 1) * pd.wt_blk[i];
+    uint2 e;
+    e.x = pass_tables_deposit(b, pd.blk_pos, pd.nblk_bits);
+    e.y = jl;
+    blk[b] = e;
+  }
+}
+
 // cudaSuccess, or the first CUDA error (tables built so far are freed).
 inline cudaError_t build_pass_tables(const Plan& plan, PassTables* out) {
   const int GB = plan.group_bits;
   cudaError_t e = cudaSuccess;
   for (const PassDesc& pd : plan.passes) {
-    const int T = pd.T, lowp = pd.T - pd.d;
-    const uint32_t t = 1u << (T - GB);
-    std::vector<uint32_t> thr((size_t)(3 + pd.nrounds) * t);
-    for (uint32_t tid = 0; tid < t; ++tid) {
-      const uint32_t lam_first = pass_tables_deposit(tid, pd.tmap[0], T - GB);
-      const uint32_t lam_last = pass_tables_deposit(tid, pd.tmap[pd.nrounds - 1], T - GB);
-      thr[tid] = pass_tables_deposit(lam_first, pd.in_pos, T);
-      thr[t + tid] = pass_tables_deposit(lam_last, pd.out_pos, T);
-      uint32_t jl = 0;
-      for (int i = 0; i < lowp; ++i) jl += ((lam_last >> i) & 1u) * pd.wt_loc[i];
-      thr[2 * t + tid] = jl;
-      for (int r = 0; r < pd.nrounds; ++r) {
-        const uint32_t lam = pass_tables_deposit(tid, pd.tmap[r], T - GB);
-        thr[(size_t)(3 + r) * t + tid] = lam | (pass_tables_swz(lam) << 16);
-      }
-    }
-    const size_t nblk = (size_t)1 << pd.nblk_bits;
-    std::vector<uint2> blk(nblk);
-    for (size_t b = 0; b < nblk; ++b) {
-      uint32_t jl = pd.jlow_const;
-      for (int i = 0; i < pd.nblk_bits; ++i) jl += (uint32_t)((b >> i) & 1) * pd.wt_blk[i];
-      blk[b] = make_uint2(pass_tables_deposit(b, pd.blk_pos, pd.nblk_bits), jl);
-    }
+    std::vector<uint32_t> thr;
+    std::vector<uint2> blk;
+    compute_pass_tables(pd, GB, &thr, &blk);
     uint32_t* d_thr = nullptr;
     uint2* d_blk = nullptr;
     if ((e = cudaMalloc((void**)&d_thr, thr.size() * 4)) != cudaSuccess) break;

@@ -162,3 +162,16 @@ def test_host_field_arithmetic_cpp(built):
     subprocess.check_call(["make", "-C", d, "hostfield_test"], stdout=subprocess.DEVNULL)
     out = subprocess.run([os.path.join(d, "hostfield_test")], capture_output=True, text=True)
     assert out.returncode == 0 and "HOSTFIELD_OK" in out.stdout, out.stdout
+
+
+def test_pass_index_tables_cpp(built):
+    """tests/cpp/pass_tables_test.cpp: the per-plan index tables the pass kernels look up instead of depositing
+    bits (csrc/pass_tables.h) describe, for every kernel shape and for the four-step pieces, a partition of the
+    data -- each element loaded once and stored once per pass, in place -- and carry the swizzle of the index they
+    name.  Host arithmetic only."""
+    import subprocess
+
+    d = os.path.join(ROOT, "tests", "cpp")
+    subprocess.check_call(["make", "-C", d, "pass_tables_test"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out = subprocess.run([os.path.join(d, "pass_tables_test")], capture_output=True, text=True)
+    assert out.returncode == 0 and "0 failures" in out.stdout, out.stdout[-2000:]
