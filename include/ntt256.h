@@ -28,7 +28,11 @@
  * batches, streams, and the multi-GPU four-step pieces (SURVEY.md par. 8e).
  *
  * Threading: a context is bound to one device and is not re-entrant.  Calls are asynchronous
- * on the given stream unless the name ends in _sync or takes host buffers.
+ * on the given stream unless the name ends in _sync or takes host buffers -- with one exception:
+ * the FIRST call of a (size, batch shape, direction) builds what it needs lazily (the pass plan and
+ * its index tables, the 1/n-scaled round table of an inverse, a streamed first-pass twiddle array)
+ * and synchronises once while doing so; such a call must not be made inside a CUDA graph capture.
+ * Later calls of the same shape only launch kernels and are capturable.
  * There is NO CPU fallback: every entry point fails with NTT256_ERR_CUDA if no sm_100 device
  * can run it.
  */
