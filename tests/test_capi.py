@@ -175,3 +175,31 @@ def test_pass_index_tables_cpp(built):
     subprocess.check_call(["make", "-C", d, "pass_tables_test"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     out = subprocess.run([os.path.join(d, "pass_tables_test")], capture_output=True, text=True)
     assert out.returncode == 0 and "0 failures" in out.stdout, out.stdout[-2000:]
+
+
+def test_headers_are_plain_c():
+    """The drop-in boundary is a C ABI: every public header compiles as C99 on its own (no C++ or torch types in a
+    signature), and the 64-bit shim of INTEGRATION.md compiles against it."""
+    import subprocess
+    import tempfile
+
+    inc = os.path.join(ROOT, "include")
+    for h in ("ntt256.h", "ntt384.h", "ntt64.h"):
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, h)])
+    shim = r'''
+#include <stdlib.h>
+#include "ntt64.h"
+void NTT_gpu(long long data[], long long reverse[], long long len, long long omega) {
+  static ntt64_ctx* ctx = 0;
+  int log_n = 0;
+  (void)reverse;
+  if (!ctx && ntt64_ctx_create(&ctx, 0, 469762049ull, (uint64_t)omega, 26)) abort();
+  while ((1ll << log_n) < len) ++log_n;
+  if (ntt64_forward_host(ctx, data, data, log_n, 1)) abort();
+}
+'''
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "shim.c")
+        with open(src, "w") as f:
+            f.write(shim)
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, "-c", src, "-o", os.path.join(d, "shim.o")])
