@@ -28,6 +28,16 @@ def plan_describe64(log_n: int, batch: int, max_log_n: int) -> dict:
     return json.loads(buf.value.decode())
 
 
+def plan_describe64_fourstep(step: int, log_n: int, log_r: int, log_p: int, rank: int, max_log_n: int) -> dict:
+    """Host-only: the plan of one local step (1 / 2 forward, 3 / 4 inverse) of the four-step decomposition."""
+    L = _load_lib()
+    a = (step, log_n, log_r, log_p, rank, max_log_n)
+    need = L.ntt64_plan_describe_fourstep(*a, None, 0)
+    buf = ctypes.create_string_buffer(need)
+    L.ntt64_plan_describe_fourstep(*a, buf, need)
+    return json.loads(buf.value.decode())
+
+
 class Ntt64:
     """ntt64_ctx: one GPU, one field (p, generator g), transforms of up to 2^max_log_n points."""
 

@@ -768,6 +768,26 @@ int ntt64_vec_mul(ntt64_ctx* ctx, void* d_out, const void* d_a, const void* d_b,
 unsigned long long ntt64_launch_count(const ntt64_ctx* ctx) { return ctx ? ctx->launches : 0; }
 const char* ntt64_last_cuda_error(const ntt64_ctx* ctx) { return ctx ? ctx->last_err.c_str() : ""; }
 
+size_t ntt64_plan_describe_fourstep(int step, int log_n, int log_r, int log_p, int rank, int max_log_n, char* buf,
+                                    size_t buf_len) {
+  ntt64_ctx tmp;  // defaults only
+  std::string s = "{\"error\": \"no plan\"}";
+  if (step >= 1 && step <= 4 && ntt256::fourstep_args_ok(log_n, log_r, log_p, rank) && log_n <= max_log_n) {
+    const bool first = (step == 1 || step == 3);
+    const ntt256::FourStepKey fk{step, log_n, log_r, log_p, first ? rank : 0};
+    int T, gb, g;
+    choose_shape(&tmp, log_n - log_p, 1, &T, &gb, &g);
+    Plan plan;
+    if (plan_for(log_n, T, gb, g, max_log_n, &plan, &fk)) s = plan.describe();
+  }
+  if (buf && buf_len) {
+    size_t m = std::min(buf_len - 1, s.size());
+    std::memcpy(buf, s.data(), m);
+    buf[m] = 0;
+  }
+  return s.size() + 1;
+}
+
 size_t ntt64_plan_describe(int log_n, int batch, int max_log_n, char* buf, size_t buf_len) {
   ntt64_ctx tmp;  // defaults only: tile / coalescing / automatic shapes
   int T, gb, g;

@@ -48,7 +48,7 @@ EXPORTS64 = [
     "ntt64_inverse_batch", "ntt64_forward_host", "ntt64_inverse_host", "ntt64_coset_forward", "ntt64_coset_inverse", "ntt64_ctx_set_coset_table_limit",
     "ntt64_fourstep_step1", "ntt64_fourstep_step1_peer", "ntt64_fourstep_step2", "ntt64_fourstep_inverse_step1",
     "ntt64_fourstep_inverse_step1_peer", "ntt64_fourstep_inverse_step2",
-    "ntt64_vec_mul", "ntt64_launch_count", "ntt64_last_cuda_error", "ntt64_plan_describe",
+    "ntt64_vec_mul", "ntt64_launch_count", "ntt64_last_cuda_error", "ntt64_plan_describe", "ntt64_plan_describe_fourstep",
 ]
 
 
@@ -186,6 +186,8 @@ def lib() -> ctypes.CDLL:
         L.ntt64_last_cuda_error.restype = ctypes.c_char_p
         L.ntt64_plan_describe.argtypes = [ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]
         L.ntt64_plan_describe.restype = ctypes.c_size_t
+        L.ntt64_plan_describe_fourstep.argtypes = [ci, ci, ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]
+        L.ntt64_plan_describe_fourstep.restype = ctypes.c_size_t
         _LIB = L
     return _LIB
 

@@ -215,3 +215,47 @@ def test_shard_layout_helpers_for_other_limb_counts():
             for k in (0, 1, n // 2 + 1, n - 1):
                 r, idx = nd.output_location(k, log_n, world)
                 assert np.array_equal(outs[r][idx], x[k])
+
+
+@pytest.mark.parametrize("log_n,world", [(8, 2), (10, 4), (12, 8), (13, 2), (16, 4)])
+def test_64_bit_fourstep_plans_execute_to_the_oracle(built, log_n, world):
+    """The four-step plans the 64-bit library runs (sixteen or four elements per thread, its own tile choice),
+    executed by the kernel model over Goldilocks: forward equals the oracle, the inverse pair returns the input
+    shards (1/n through the scaled round table or the output scale, as the library does it)."""
+    from ntt_b200.api64 import plan_describe64_fourstep
+
+    F = po.Field("goldilocks", 0xFFFFFFFF00000001, 7)
+    max_log_n = 16
+    log_p, log_r = world.bit_length() - 1, nd.default_log_r(log_n)
+    w_max = pow(F.g, (F.p - 1) >> max_log_n, F.p)
+    rng = random.Random(64 * log_n + world)
+    x = [rng.randrange(F.p) for _ in range(1 << log_n)]
+    want = po.ntt_ref(x, F)
+
+    def run(step, shard, rank, inverse=False):
+        plan = plan_describe64_fourstep(step, log_n, log_r, log_p, rank, max_log_n)
+        assert "error" not in plan and plan["group_bits"] in (2, 4)
+        data = [int(v) for v in shard]
+        passes = plan["passes"]
+        for i, pd in enumerate(passes):
+            pd = dict(pd)
+            scale = None
+            if step == 4 and i == len(passes) - 1:
+                scale = pow(1 << log_n, F.p - 2, F.p)
+                if pd["nrounds"] >= 2:
+                    pd["scaled_round"] = 0
+                else:
+                    pd["scale_out"] = 1
+            plan_sim.run_pass(data, pd, F.p, w_max, max_log_n, inverse, scale, group_bits=plan["group_bits"])
+        return np.array(data, dtype=np.uint64).reshape(-1, 1)
+
+    xs = np.array(x, dtype=np.uint64).reshape(-1, 1)
+    ins = nd.scatter_input(xs, log_n, world, log_r, limbs=1)
+    s1 = [run(1, s.reshape(-1), r) for r, s in enumerate(ins)]
+    s2 = [run(2, s.reshape(-1), r) for r, s in enumerate(nd.exchange_reference(s1, world))]
+    got = nd.gather_output(s2, log_n, world, log_r, limbs=1).reshape(-1)
+    assert [int(v) for v in got] == want
+    b1 = [run(3, s.reshape(-1), r, inverse=True) for r, s in enumerate(s2)]
+    b2 = [run(4, s.reshape(-1), r, inverse=True) for r, s in enumerate(nd.exchange_reference(b1, world))]
+    for r in range(world):
+        assert np.array_equal(b2[r], ins[r]), r
