@@ -82,6 +82,9 @@ unsigned long long ntt384_launch_count(const ntt384_ctx* ctx);
 const char* ntt384_last_cuda_error(const ntt384_ctx* ctx);
 /* Host-only: JSON description of the pass plan for 2^log_n points (size returned, like ntt256_plan_describe). */
 size_t ntt384_plan_describe(int log_n, int max_log_n, char* buf, size_t buf_len);
+/* The same for one local step of the four-step decomposition (step 1 / 2 forward, 3 / 4 inverse) on `rank`. */
+size_t ntt384_plan_describe_fourstep(int step, int log_n, int log_r, int log_p, int rank, int max_log_n, char* buf,
+                                     size_t buf_len);
 
 #ifdef __cplusplus
 }

@@ -601,6 +601,37 @@ int ntt384_vec_mul(ntt384_ctx* ctx, void* d_out, const void* d_a, const void* d_
 unsigned long long ntt384_launch_count(const ntt384_ctx* ctx) { return ctx ? ctx->launches : 0; }
 const char* ntt384_last_cuda_error(const ntt384_ctx* ctx) { return ctx ? ctx->last_err.c_str() : ""; }
 
+size_t ntt384_plan_describe_fourstep(int step, int log_n, int log_r, int log_p, int rank, int max_log_n, char* buf,
+                                     size_t buf_len) {
+  std::string s = "{\"error\": \"no plan\"}";
+  if (step >= 1 && step <= 4 && fourstep_args_ok(log_n, log_r, log_p, rank) && log_n <= max_log_n) {
+    const bool first = (step == 1 || step == 3);
+    const int nloc = log_n - log_p;
+    // the request get_plan() makes for this piece with the default tuning
+    PlanRequest req = fourstep_request(FourStepKey{step, log_n, log_r, log_p, first ? rank : 0}, std::min(kTileBits384, nloc), 0,
+                                       max_log_n);
+    req.coalesce_bits = std::min(kCoalesce384, req.tile_bits);
+    req.group_bits = 2;
+    Plan plan;
+    bool ok = make_plan(req, &plan);
+    for (int g = req.coalesce_bits - 1; !ok && g >= 0; --g) {
+      req.coalesce_bits = g;
+      ok = make_plan(req, &plan, 12);
+    }
+    for (int t = req.tile_bits + 1; !ok && t <= 11; ++t) {
+      req.tile_bits = t;
+      ok = make_plan(req, &plan, 12);
+    }
+    if (ok) s = plan.describe();
+  }
+  if (buf && buf_len) {
+    size_t m = std::min(buf_len - 1, s.size());
+    std::memcpy(buf, s.data(), m);
+    buf[m] = 0;
+  }
+  return s.size() + 1;
+}
+
 size_t ntt384_plan_describe(int log_n, int max_log_n, char* buf, size_t buf_len) {
   PlanRequest req;
   req.log_n = log_n;

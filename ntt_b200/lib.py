@@ -38,7 +38,7 @@ EXPORTS384 = [
     "ntt384_inverse_batch", "ntt384_forward_host", "ntt384_inverse_host", "ntt384_coset_forward", "ntt384_coset_inverse",
     "ntt384_forward_mul", "ntt384_inverse_mul", "ntt384_fourstep_step1", "ntt384_fourstep_step1_peer", "ntt384_fourstep_step2",
     "ntt384_fourstep_inverse_step1", "ntt384_fourstep_inverse_step1_peer", "ntt384_fourstep_inverse_step2",
-    "ntt384_ctx_set_peer_sync", "ntt384_vec_mul", "ntt384_launch_count", "ntt384_last_cuda_error", "ntt384_plan_describe",
+    "ntt384_ctx_set_peer_sync", "ntt384_vec_mul", "ntt384_launch_count", "ntt384_last_cuda_error", "ntt384_plan_describe", "ntt384_plan_describe_fourstep",
 ]
 
 
@@ -160,6 +160,8 @@ def lib() -> ctypes.CDLL:
         L.ntt384_last_cuda_error.restype = ctypes.c_char_p
         L.ntt384_plan_describe.argtypes = [ci, ci, ctypes.c_char_p, ctypes.c_size_t]
         L.ntt384_plan_describe.restype = ctypes.c_size_t
+        L.ntt384_plan_describe_fourstep.argtypes = [ci, ci, ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_size_t]
+        L.ntt384_plan_describe_fourstep.restype = ctypes.c_size_t
         u64 = ctypes.c_uint64
         L.ntt64_ctx_create.argtypes = [ctypes.POINTER(vp), ci, u64, u64, ci]
         L.ntt64_ctx_destroy.argtypes = [vp]
@@ -214,6 +216,18 @@ def plan_describe_fourstep(step: int, log_n: int, log_r: int, log_p: int, rank: 
     need = L.ntt256_plan_describe_fourstep(*a, None, 0)
     buf = ctypes.create_string_buffer(need)
     L.ntt256_plan_describe_fourstep(*a, buf, need)
+    return json.loads(buf.value.decode())
+
+
+def plan_describe_384_fourstep(step: int, log_n: int, log_r: int, log_p: int, rank: int, max_log_n: int) -> dict:
+    """Host-only: the plan of one local step (1 / 2 forward, 3 / 4 inverse) of the 384-bit four-step decomposition."""
+    import json
+
+    L = lib()
+    a = (step, log_n, log_r, log_p, rank, max_log_n)
+    need = L.ntt384_plan_describe_fourstep(*a, None, 0)
+    buf = ctypes.create_string_buffer(need)
+    L.ntt384_plan_describe_fourstep(*a, buf, need)
     return json.loads(buf.value.decode())
 
 

@@ -259,3 +259,47 @@ def test_64_bit_fourstep_plans_execute_to_the_oracle(built, log_n, world):
     b2 = [run(4, s.reshape(-1), r, inverse=True) for r, s in enumerate(nd.exchange_reference(b1, world))]
     for r in range(world):
         assert np.array_equal(b2[r], ins[r]), r
+
+
+@pytest.mark.parametrize("log_n,world", [(8, 2), (10, 4), (12, 8)])
+def test_384_bit_fourstep_plans_execute_to_the_oracle(built, log_n, world):
+    """The four-step plans the 384-bit library runs (four elements per thread, 2^9-element tiles), executed by the
+    kernel model over BLS12-377 Fq: forward equals the oracle, the inverse pair returns the input shards."""
+    from ntt_b200.lib import plan_describe_384_fourstep
+
+    F = po.BLS12_377_FQ
+    max_log_n = 14
+    log_p, log_r = world.bit_length() - 1, nd.default_log_r(log_n)
+    w_max = pow(F.g, (F.p - 1) >> max_log_n, F.p)
+    rng = random.Random(384 * log_n + world)
+    x = [rng.randrange(F.p) for _ in range(1 << log_n)]
+    want = po.ntt_ref(x, F)
+
+    def run(step, shard, rank, inverse=False):
+        plan = plan_describe_384_fourstep(step, log_n, log_r, log_p, rank, max_log_n)
+        assert "error" not in plan and plan["group_bits"] == 2
+        data = list(shard)
+        passes = plan["passes"]
+        for i, pd in enumerate(passes):
+            pd = dict(pd)
+            scale = None
+            if step == 4 and i == len(passes) - 1:
+                scale = pow(1 << log_n, F.p - 2, F.p)
+                if pd["nrounds"] >= 2:
+                    pd["scaled_round"] = 0
+                else:
+                    pd["scale_out"] = 1
+            plan_sim.run_pass(data, pd, F.p, w_max, max_log_n, inverse, scale, group_bits=2)
+        return data
+
+    # shards as Python integers: the layout helpers work on any [n, limbs] array, object dtype included
+    xs = np.array(x, dtype=object).reshape(-1, 1)
+    ins = nd.scatter_input(xs, log_n, world, log_r, limbs=1)
+    s1 = [np.array(run(1, list(s.reshape(-1)), r), dtype=object).reshape(-1, 1) for r, s in enumerate(ins)]
+    s2 = [np.array(run(2, list(s.reshape(-1)), r), dtype=object).reshape(-1, 1)
+          for r, s in enumerate(nd.exchange_reference(s1, world))]
+    assert list(nd.gather_output(s2, log_n, world, log_r, limbs=1).reshape(-1)) == want
+    b1 = [np.array(run(3, list(s.reshape(-1)), r, inverse=True), dtype=object).reshape(-1, 1) for r, s in enumerate(s2)]
+    b2 = [run(4, list(s.reshape(-1)), r, inverse=True) for r, s in enumerate(nd.exchange_reference(b1, world))]
+    for r in range(world):
+        assert b2[r] == list(ins[r].reshape(-1)), r
