@@ -1,4 +1,5 @@
-// Device kernels of the self-sorting in-place 256-bit NTT (sm_100a).
+// Device kernels of the self-sorting in-place 256-bit NTT (sm_100a): the 8-limb field policies (F256<SH>:
+// Montgomery or Shoup twiddles) of the one pass body in ntt_pass_generic.cuh, and their kernel instances.
 //
 //   ntt_pass_kernel   one pass of the plan (plan.h): a CTA owns a tile of 2^T elements picked
 //                     by T index bits, each thread keeps 8 elements in registers, runs up to
