@@ -117,6 +117,21 @@ def test_oracle64_against_compiled_reference_and_python(built):
         assert np.array_equal(co.ntt64(c, GL.p, GL.g, inverse=True, threads=2), x)
 
 
+def test_oracle64_reproduces_the_goldilocks_known_answers(built):
+    """tests/golden/goldilocks_kat.json (made by the Python oracle, scripts/gen_golden64.py): the C 64-bit oracle --
+    the checker of the Goldilocks GPU path -- gives the same digests, single- and multi-threaded."""
+    g = _load("goldilocks_kat.json")
+    for case in g["cases"]:
+        n = 1 << case["log_n"]
+        x = np.arange(n, dtype=np.uint64) if case["input"] == "iota" else co.splitmix64_elements(n, g["p"], case["seed"])
+        for threads in (1, 3):
+            X = co.ntt64(x, g["p"], g["g"], threads=threads)
+            assert hashlib.sha256(X.astype("<u8").tobytes()).hexdigest() == case["sha256_u64le"], case
+            assert [int(v) for v in X[:4]] == case["head"][: min(4, n)]
+            if "full" in case:
+                assert [int(v) for v in X] == case["full"]
+
+
 def test_bigfield_golden(built):
     g = _load("bigfield_kat.json")
     for case in g["cases"]:
